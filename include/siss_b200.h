@@ -1,0 +1,214 @@
+/*
+ * siss_b200.h — C ABI of libsiss_b200.so: the B200 (sm_100a) kernels behind the SISS
+ * data-unlearning hot path.
+ *
+ * The reference (claserken/SISS) is pure Python/PyTorch: it has no FFI of its own, so each entry
+ * point below cites the reference *call site* whose sequence of ATen launches it replaces
+ * (paths relative to the reference checkout). The Python host layer (siss_b200/) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless the
+ *     parameter name starts with `h_`;
+ *   - tensors are contiguous, row-major `[B, D]` with D = C*H*W (NCHW flattened per sample);
+ *   - `dtype` / `pred_dtype` are SISS_F32 / SISS_BF16 / SISS_F16;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all entry points are asynchronous w.r.t. the host and never synchronise the device;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative SISS_E* code.
+ *     `siss_error_string` renders either.
+ *   - reductions are fixed-order: results are bitwise reproducible run to run for a given
+ *     shape on a given GPU.
+ */
+#ifndef SISS_B200_H
+#define SISS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SISS_B200_ABI_VERSION 1
+
+enum siss_dtype { SISS_F32 = 0, SISS_BF16 = 1, SISS_F16 = 2 };
+
+enum siss_status {
+    SISS_OK = 0,
+    SISS_EINVAL = -1,       /* null pointer / non-positive size / bad enum            */
+    SISS_EUNSUPPORTED = -2, /* dtype combination not compiled in                       */
+    SISS_EARCH = -3         /* device is not sm_100 (this library has no other target) */
+};
+
+enum siss_combine_mode {
+    SISS_COMBINE_SCALING_NORM = 0, /* s = scaling_norm / ||g_a||        (delete_celeb.py:746)     */
+    SISS_COMBINE_ERASEDIFF = 1,    /* s = -max(eta - <g_x,g_a>/||g_a||^2, 0)  (delete_celeb.py:741-742) */
+    SISS_COMBINE_NONE = 2          /* s = 0: single-loss methods, only the clip applies (delete_celeb.py:682-684,767) */
+};
+
+typedef void* siss_stream_t;
+
+int siss_abi_version(void);
+const char* siss_error_string(int code);
+/* Fails with SISS_EARCH unless the current device is compute capability 10.x. */
+int siss_check_device(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 — DDPM forward noising  x_t = sqrt(abar_t) * x0 + sqrt(1 - abar_t) * eps
+ * Replaces diffusers==0.27.2 `DDPMScheduler.add_noise` as called at delete_celeb.py:602-603,
+ * delete_tshirt.py:544-545, delete_sd.py:922-934. `alphas_cumprod` is the fp32 table [T]; it is
+ * cast to `dtype` BEFORE the square roots and every product / the sum is rounded to `dtype`,
+ * which is the eager rounding sequence. The pair form shares eps and t between the keep batch
+ * (x0) and the forget batch (a0) as the reference does (delete_celeb.py:579-603).
+ * Algorithmic bytes/element: single 3*s, pair 5*s  (s = sizeof dtype).
+ * ---------------------------------------------------------------------------------------- */
+int siss_add_noise(const void* x0, const void* noise, const int64_t* timesteps,
+                   const float* alphas_cumprod, int T, void* xt,
+                   int64_t B, int64_t D, int dtype, siss_stream_t stream);
+
+int siss_add_noise_pair(const void* x0, const void* a0, const void* noise, const int64_t* timesteps,
+                        const float* alphas_cumprod, int T, void* xt_x, void* xt_a,
+                        int64_t B, int64_t D, int dtype, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Workspace for the per-sample (row) reductions of K2 / K3. Allocate once, ZERO it once
+ * (cudaMemset) and reuse: the kernels leave their ticket counters reset. Size depends only on
+ * the largest B it will be used with.
+ * ---------------------------------------------------------------------------------------- */
+int64_t siss_row_workspace_bytes(int64_t B);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 — defensive-mixture sampling + importance weights.
+ * Replaces losses/ddpm_deletion_loss.py:12-23 (gamma/sigma gather, Bernoulli row select) and
+ * :32-45 (Gaussian exponents d_x, d_a and the two importance weights).
+ *   keep_mask[b] != 0  -> row b of x_mix is taken from the keep batch, else from the forget batch
+ *                        (the host draws it exactly as the reference: CPU `torch.rand(B) > lambd`).
+ *   dist_x[b] = sum_D (x_mix - gamma_t x0)^2 / (2 sigma_t^2),  dist_a likewise with a0
+ *   w_x[b] = 1 / ((1-lambd) + lambd * exp(dist_x - dist_a))
+ *   w_a[b] = 1 / ((1-lambd) * exp(dist_a - dist_x) + lambd)
+ * The exponent difference is accumulated directly (sum of (r_x - r_a)(r_x + r_a)) instead of
+ * subtracting two ~D/2-sized fp32 sums, then fed through the reference's literal formula, so the
+ * inf/0 saturation of the weights is reproduced ("importance weights").
+ * Algorithmic bytes/element: 4*s (selected x_t row, x0, a0 read; x_mix written).
+ * ---------------------------------------------------------------------------------------- */
+int siss_mixture_weights(const void* xt_x, const void* xt_a, const void* x0, const void* a0,
+                         const uint8_t* keep_mask, const int64_t* timesteps,
+                         const float* gamma, const float* sigma, int T, double lambd,
+                         void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
+                         void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream);
+
+/* K1 o K2 fused: x_t is formed only for the selected source and never written for the other.
+ * Same outputs as siss_mixture_weights. Algorithmic bytes/element: 4*s (x0, a0, eps read; x_mix
+ * written). */
+int siss_add_noise_mixture(const void* x0, const void* a0, const void* noise,
+                           const uint8_t* keep_mask, const int64_t* timesteps,
+                           const float* alphas_cumprod, const float* gamma, const float* sigma, int T,
+                           double lambd,
+                           void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
+                           void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 — weighted epsilon-MSE.
+ * Replaces losses/ddpm_deletion_loss.py:26-30 (targets eps_x, eps_a and squared errors), :51-53
+ * (importance weighting), the scalarisation at delete_celeb.py:686-687 and autograd's backward
+ * of all of that into the UNet output (delete_celeb.py:691,702).
+ *   eps_x = (x_mix - gamma_t x0) / sigma_t     eps_a = (x_mix - gamma_t a0) / sigma_t   (fp32)
+ *   loss_x = (pred - eps_x)^2                  loss_a = (pred - eps_a)^2
+ *
+ * siss_wmse_fwd_bwd (fast path): one pass that emits BOTH upstream gradients
+ *   grad_x = (go_x * w_x[b]) * (2 (pred - eps_x))   grad_a = (go_a * w_a[b]) * (2 (pred - eps_a))
+ * in pred's dtype, plus per-sample sums row_loss_{x,a}[b] = sum_D loss_{x,a} (for the stats block
+ * delete_celeb.py:626-663). go_x / go_a are d(total)/d(weighted_loss element), i.e.
+ * 1/(train_batch_size * grad_accum) in the reference. Nothing [B,D]-sized is materialised except
+ * the two gradients. Algorithmic bytes/element: sizeof(pred) + 3*s + 2*sizeof(pred).
+ * ---------------------------------------------------------------------------------------- */
+int siss_wmse_fwd_bwd(const void* pred, int pred_dtype,
+                      const void* x_mix, const void* x0, const void* a0, int dtype,
+                      const int64_t* timesteps, const float* gamma, const float* sigma, int T,
+                      const float* w_x, const float* w_a, float go_x, float go_a,
+                      void* grad_x, void* grad_a, float* row_loss_x, float* row_loss_a,
+                      void* workspace, int64_t B, int64_t D, siss_stream_t stream);
+
+/* API-compatible forward: materialises the four fp32 [B,D] tensors of the reference 7-tuple
+ * (losses/ddpm_deletion_loss.py:56). Any of the four outputs may be NULL (skipped). */
+int siss_wmse_fwd(const void* pred, int pred_dtype,
+                  const void* x_mix, const void* x0, const void* a0, int dtype,
+                  const int64_t* timesteps, const float* gamma, const float* sigma, int T,
+                  const float* w_x, const float* w_a,
+                  float* loss_x, float* loss_a, float* wloss_x, float* wloss_a,
+                  int64_t B, int64_t D, siss_stream_t stream);
+
+/* API-compatible backward: grad_pred = sum over the present upstream gradients of
+ *   go_loss_x * 2u_x + (go_wloss_x * w_x) * 2u_x + go_loss_a * 2u_a + (go_wloss_a * w_a) * 2u_a.
+ * Each go_* is NULL (absent), a [B,D] fp32 tensor (stride 1) or one broadcast fp32 scalar in
+ * device memory (stride 0: what autograd hands back for `.sum()`), selected by *_stride. */
+int siss_wmse_bwd(const void* pred, int pred_dtype,
+                  const void* x_mix, const void* x0, const void* a0, int dtype,
+                  const int64_t* timesteps, const float* gamma, const float* sigma, int T,
+                  const float* w_x, const float* w_a,
+                  const float* go_loss_x, int go_loss_x_stride,
+                  const float* go_loss_a, int go_loss_a_stride,
+                  const float* go_wloss_x, int go_wloss_x_stride,
+                  const float* go_wloss_a, int go_wloss_a_stride,
+                  void* grad_pred, int64_t B, int64_t D, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Plain squared error against a given target — the No-IS / EraseDiff / NegGrad / naive losses,
+ * losses/ddpm_deletion_loss.py:60-96:  loss = (pred - target)^2 ; scaled = alpha * loss.
+ * Output dtype is the torch promotion of (pred, target): fp32 unless both are the same 16-bit
+ * type, in which case every op rounds to that type like eager does.
+ * ---------------------------------------------------------------------------------------- */
+int siss_sqerr_fwd(const void* pred, int pred_dtype, const void* target, int target_dtype,
+                   void* loss, void* scaled /* nullable */, float alpha,
+                   int64_t n, siss_stream_t stream);
+
+/* grad_pred = go_loss * 2u + (go_scaled * alpha) * 2u ; go_* as in siss_wmse_bwd (fp32 or the
+ * promoted 16-bit type, given by go_dtype). */
+int siss_sqerr_bwd(const void* pred, int pred_dtype, const void* target, int target_dtype,
+                   const void* go_loss, int go_loss_stride,
+                   const void* go_scaled, int go_scaled_stride, float alpha, int go_dtype,
+                   void* grad_pred, int64_t n, siss_stream_t stream);
+
+/* Fast path for double_forward_with_neg_del / erasediff: both squared errors, both gradients
+ * (grad = go * 2 (pred - target), in pred's dtype) and per-sample sums in one pass.
+ * target_a may equal target_x (No-IS shares eps); it is then read once.
+ * Algorithmic bytes/element (fp32, shared target): 3 reads + 2 writes = 20. */
+int siss_dual_mse_fwd_bwd(const void* pred_x, const void* pred_a, int pred_dtype,
+                          const void* target_x, const void* target_a, int target_dtype,
+                          float go_x, float go_a, void* grad_x, void* grad_a,
+                          float* row_loss_x, float* row_loss_a,
+                          void* workspace, int64_t B, int64_t D, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 — two-term gradient combine on flat fp32 buffers.
+ * Replaces the per-parameter Python loops at delete_celeb.py:714-753 (= delete_tshirt.py:656-697,
+ * delete_sd.py:1071-1109) and the clip at delete_celeb.py:767.
+ *
+ * K4a siss_norm3: sums3 = { sum g_x^2, sum g_a^2, sum g_x*g_a } as three doubles (fp32 products,
+ * fp64 accumulation, fixed order). 8 bytes/parameter. `workspace` from siss_norm3_workspace_bytes,
+ * zeroed once.
+ *
+ * K4b siss_combine: reads sums3 FROM DEVICE MEMORY (so an all-reduce of the three scalars can sit
+ * between K4a and K4b with no host sync) and writes
+ *     out = clip * (g_x - s * g_a)
+ *   s    per `mode` (see siss_combine_mode); if inf_guard and s is inf, s = 0 (delete_tshirt.py:688-690)
+ *   clip = min(1, max_norm / (||g_x - s g_a|| + 1e-6))   (torch.nn.utils.clip_grad_norm_);
+ *          max_norm <= 0 disables it. The norm of the combination is obtained algebraically from
+ *          sums3: ||g_x||^2 - 2 s <g_x,g_a> + s^2 ||g_a||^2, evaluated in fp64.
+ *   stats5 (nullable) = { ||g_x||, ||g_a||, s, ||g_x - s g_a||, clip } — the three wandb scalars
+ *          of delete_celeb.py:748 plus what clip_grad_norm_ returns.
+ *   `out` may alias g_x or g_a. 12 bytes/parameter.
+ * ---------------------------------------------------------------------------------------- */
+int64_t siss_norm3_workspace_bytes(void);
+
+int siss_norm3(const float* g_x, const float* g_a, int64_t n, double* sums3,
+               void* workspace, siss_stream_t stream);
+
+int siss_combine(const float* g_x, const float* g_a, float* out, int64_t n,
+                 const double* sums3, int mode, float value, float max_norm, int inf_guard,
+                 float* stats5, siss_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SISS_B200_H */

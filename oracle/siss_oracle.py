@@ -1,0 +1,326 @@
+"""CPU oracle for the SISS hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this module, and only as the checker / the timed CPU baseline. Nothing under
+``siss_b200/`` imports it; the product path has no CPU fallback.
+
+What it is: a restatement, in eager PyTorch on CPU tensors (the reference's own runtime, so dtype
+promotion and bf16 rounding are the reference's), of
+
+  * ``losses/ddpm_deletion_loss.py`` (all six methods)                      -> ``OracleDeletionLoss``
+  * diffusers==0.27.2 ``DDPMScheduler`` betas / ``alphas_cumprod`` / ``add_noise``
+    (third-party, pinned at environment.yml:232, NOT present under /root/reference and not
+    installed here; restated from that release's published algorithm)     -> ``make_alphas_cumprod``, ``add_noise``
+  * the inline two-backward + gradient-combine block, delete_celeb.py:682-767
+    (tshirt inf-guard delete_tshirt.py:688-690)                           -> ``reference_grad_step``
+  * ``accelerator.backward`` (loss / gradient_accumulation_steps, accelerate==0.27.2) and
+    ``accelerator.clip_grad_norm_`` (= ``torch.nn.utils.clip_grad_norm_``, called directly).
+
+Parity pinning:
+  * loss class: PINNED — tests/golden/*.npz are outputs of the reference's own file executed from
+    /root/reference by tests/golden/make_golden.py; tests/test_oracle_golden.py checks this module
+    against them bit for bit.
+  * add_noise, accelerate.backward scaling, combine block: the reference holds no test, fixture or
+    golden vector for them and their third-party halves are absent: PARITY UNPINNED at that
+    boundary. The combine restatement is additionally cross-checked against real autograd on a
+    small module (tests/test_oracle_golden.py::test_combine_matches_literal_loop).
+
+Every function is dtype-generic: call it with float64 tensors to get the "exact" answer the fp32
+results are compared against.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------------
+# Noise schedule and add_noise (diffusers 0.27.2 DDPMScheduler; call sites delete_celeb.py:602-603)
+# --------------------------------------------------------------------------------------------------
+def make_alphas_cumprod(num_train_timesteps: int = 1000, beta_start: float = 1e-4, beta_end: float = 0.02,
+                        beta_schedule: str = "linear") -> Tensor:
+    """fp32 cumulative product of (1 - beta). ``linear`` is the DDPM/celebahq/tshirt schedule
+    (config/train_tshirt_mnist.yaml:43-50), ``scaled_linear`` is Stable Diffusion's."""
+    if beta_schedule == "linear":
+        betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+    elif beta_schedule == "scaled_linear":
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    else:
+        raise NotImplementedError(beta_schedule)
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def gamma_sigma(alphas_cumprod: Tensor) -> Tuple[Tensor, Tensor]:
+    """delete_celeb.py:367-371: gamma = abar**0.5, sigma = (1 - abar)**0.5 (fp32 tables)."""
+    return alphas_cumprod ** 0.5, (1 - alphas_cumprod) ** 0.5
+
+
+def add_noise(alphas_cumprod: Tensor, original_samples: Tensor, noise: Tensor, timesteps: Tensor) -> Tensor:
+    """DDPMScheduler.add_noise: the table is cast to the SAMPLE dtype first, then gathered, then
+    square-rooted; the two products and the sum are ordinary eager ops in the sample dtype."""
+    ac = alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+    timesteps = timesteps.to(original_samples.device)
+    sqrt_alpha_prod = (ac[timesteps] ** 0.5).flatten()
+    while sqrt_alpha_prod.dim() < original_samples.dim():
+        sqrt_alpha_prod = sqrt_alpha_prod.unsqueeze(-1)
+    sqrt_one_minus = ((1 - ac[timesteps]) ** 0.5).flatten()
+    while sqrt_one_minus.dim() < original_samples.dim():
+        sqrt_one_minus = sqrt_one_minus.unsqueeze(-1)
+    return sqrt_alpha_prod * original_samples + sqrt_one_minus * noise
+
+
+# --------------------------------------------------------------------------------------------------
+# Loss class (losses/ddpm_deletion_loss.py)
+# --------------------------------------------------------------------------------------------------
+def _bcast(v: Tensor, like: Tensor) -> Tensor:
+    return v.reshape(v.shape[0], *([1] * (like.dim() - 1)))
+
+
+def draw_keep_mask(batch_size: int, lambd: float) -> Tensor:
+    """ddpm_deletion_loss.py:18 — CPU default-generator uniform draw; True = keep-batch row."""
+    return torch.rand(batch_size) > lambd
+
+
+def select_mixture(noisy_keep: Tensor, noisy_forget: Tensor, keep_mask: Tensor) -> Tensor:
+    """ddpm_deletion_loss.py:19-23 — row select."""
+    mix = torch.empty_like(noisy_keep)
+    forget_mask = ~keep_mask
+    mix[keep_mask] = noisy_keep[keep_mask]
+    mix[forget_mask] = noisy_forget[forget_mask]
+    return mix
+
+
+def gaussian_exponents(mix: Tensor, x0: Tensor, a0: Tensor, gamma_t: Tensor, sigma_t: Tensor) -> Tuple[Tensor, Tensor]:
+    """ddpm_deletion_loss.py:31-39 — d = ||x_t - gamma x0||^2 / (2 sigma^2), summed over all but dim 0."""
+    dims = list(range(1, mix.dim()))
+    g = _bcast(gamma_t, mix)
+    d_x = torch.sum((mix - g * x0) ** 2, dim=dims)
+    d_x = d_x / (2 * (sigma_t ** 2))
+    d_a = torch.sum((mix - g * a0) ** 2, dim=dims)
+    d_a = d_a / (2 * (sigma_t ** 2))
+    return d_x, d_a
+
+
+def importance_weights(d_x: Tensor, d_a: Tensor, lambd: float) -> Tuple[Tensor, Tensor]:
+    """ddpm_deletion_loss.py:41-45."""
+    r_ax = torch.exp(d_x - d_a)
+    r_xa = torch.exp(d_a - d_x)
+    w_x = 1 / ((1 - lambd) + lambd * r_ax)
+    w_a = 1 / ((1 - lambd) * r_xa + lambd)
+    return w_x, w_a
+
+
+class OracleDeletionLoss:
+    """Restatement of DDPMDeletionLoss; same constructor, method names, parameters and 7-tuples.
+    ``keep_mask`` is an extra optional argument so tests can share one draw between oracle and kernel."""
+
+    def __init__(self, gamma: Tensor, sigma: Tensor):
+        self.all_gamma = gamma
+        self.all_sigma = sigma
+
+    def importance_sampling_with_mixture(self, unet, timesteps, noise, conditioning, all_samples_dict,
+                                         deletion_samples_dict, lambd, keep_mask: Optional[Tensor] = None):
+        g_t = self.all_gamma[timesteps]
+        s_t = self.all_sigma[timesteps]
+        noisy_keep, noisy_forget = all_samples_dict['noisy_latents'], deletion_samples_dict['noisy_latents']
+        x0, a0 = all_samples_dict['og_latents'], deletion_samples_dict['og_latents']
+        if keep_mask is None:
+            keep_mask = draw_keep_mask(noisy_keep.shape[0], lambd)
+        mix = select_mixture(noisy_keep, noisy_forget, keep_mask)
+        pred = unet(mix, timesteps, **conditioning, return_dict=False)[0]
+
+        eps_x = (mix - _bcast(g_t, mix) * x0) / _bcast(s_t, mix)     # :26
+        eps_a = (mix - _bcast(g_t, mix) * a0) / _bcast(s_t, mix)     # :27
+        loss_x = (pred - eps_x) ** 2                                  # :29
+        loss_a = (pred - eps_a) ** 2                                  # :30
+        d_x, d_a = gaussian_exponents(mix, x0, a0, g_t, s_t)          # :32-39
+        w_x, w_a = importance_weights(d_x, d_a, lambd)                # :41-45
+        wl_x = _bcast(w_x, loss_x) * loss_x                           # :51
+        wl_a = _bcast(w_a, loss_a) * loss_a                           # :53
+        return None, loss_x, loss_a, w_x, w_a, wl_x, wl_a
+
+    def double_forward_with_neg_del(self, unet, timesteps, noise, conditioning, all_samples_dict,
+                                    deletion_samples_dict):
+        pred_x = unet(all_samples_dict['noisy_latents'], timesteps, **conditioning, return_dict=False)[0]
+        loss_x = (pred_x - noise) ** 2
+        pred_a = unet(deletion_samples_dict['noisy_latents'], timesteps, **conditioning, return_dict=False)[0]
+        loss_a = (pred_a - noise) ** 2
+        return None, loss_x, loss_a, None, None, loss_x, loss_a
+
+    def erasediff(self, unet, timesteps, noise, conditioning, all_samples_dict, deletion_samples_dict,
+                  uniform_noise: Optional[Tensor] = None):
+        pred_x = unet(all_samples_dict['noisy_latents'], timesteps, **conditioning, return_dict=False)[0]
+        loss_x = (pred_x - noise) ** 2
+        pred_a = unet(deletion_samples_dict['noisy_latents'], timesteps, **conditioning, return_dict=False)[0]
+        if uniform_noise is None:
+            uniform_noise = torch.rand_like(pred_a)                   # :75, drawn after forward #2
+        loss_a = (pred_a - uniform_noise) ** 2
+        return None, loss_x, loss_a, None, None, loss_x, loss_a
+
+    def simple_neg_del(self, unet, timesteps, noise, conditioning, all_samples_dict, deletion_samples_dict,
+                       superfactor):
+        pred_a = unet(deletion_samples_dict['noisy_latents'], timesteps, **conditioning, return_dict=False)[0]
+        loss_a = (pred_a - noise) ** 2
+        loss = -superfactor * loss_a
+        return loss, None, loss_a, None, None, None, None
+
+    def naive_del(self, unet, timesteps, noise, conditioning, all_samples_dict, deletion_samples_dict):
+        pred_x = unet(all_samples_dict['noisy_latents'], timesteps, **conditioning, return_dict=False)[0]
+        loss_x = (pred_x - noise) ** 2
+        return loss_x, loss_x, None, None, None, None, None
+
+    def subscore_bernoulli(self, unet, timesteps, noise, conditioning, all_samples_dict, deletion_samples_dict,
+                           lambd, keep_mask: Optional[Tensor] = None):
+        noisy_keep, noisy_forget = all_samples_dict['noisy_latents'], deletion_samples_dict['noisy_latents']
+        if keep_mask is None:
+            keep_mask = draw_keep_mask(noisy_keep.shape[0], lambd)
+        forget_mask = ~keep_mask
+        mix = select_mixture(noisy_keep, noisy_forget, keep_mask)
+        pred = unet(mix, timesteps, **conditioning, return_dict=False)[0]
+        loss = (pred - noise) ** 2
+        loss_x = (1 / (1 - lambd)) * loss[keep_mask]
+        loss_a = loss[forget_mask]
+        if len(loss_x) == 0:                                          # :113-116
+            loss_x = torch.zeros(1, 1, 1, 1, requires_grad=True)
+            loss_a = torch.zeros(1, 1, 1, 1, requires_grad=True)
+        if len(loss_a) == 0:                                          # :118-120
+            loss_a = torch.zeros(1, 1, 1, 1, requires_grad=True)
+        return None, loss_x, loss_a, None, None, loss_x, loss_a
+
+
+# --------------------------------------------------------------------------------------------------
+# Two backward passes + gradient combine (delete_celeb.py:682-767)
+# --------------------------------------------------------------------------------------------------
+def accelerate_backward(loss: Tensor, grad_accum_steps: int, retain_graph: bool = False) -> None:
+    """accelerate==0.27.2 ``Accelerator.backward`` without a scaler: divide by the accumulation
+    steps, then ``.backward()``."""
+    (loss / grad_accum_steps).backward(retain_graph=retain_graph)
+
+
+class ReferenceGradLoop:
+    """The reference's inline gradient bookkeeping for one optimiser step, restated around an
+    ``nn.Module``: per-parameter dicts keyed by name, clones and subtractions included, so the op
+    and rounding order is the reference's. Use: ``micro_step`` G times, then ``sync_step``."""
+
+    def __init__(self, model: torch.nn.Module, train_batch_size: int, grad_accum_steps: int = 1):
+        self.model = model
+        self.train_batch_size = train_batch_size
+        self.grad_accum_steps = grad_accum_steps
+        self.accum_loss_x: Dict[str, Tensor] = {}
+        self.accum_loss_a: Dict[str, Tensor] = {}
+
+    def micro_step(self, items: Sequence[Optional[Tensor]], retain_graph: bool) -> None:
+        loss, _lx, _la, _wx, _wa, weighted_loss_x, weighted_loss_a = items
+        if loss is not None:                                                          # :682-684
+            accelerate_backward(loss.sum() / self.train_batch_size, self.grad_accum_steps)
+            return
+        wl_x = weighted_loss_x.sum() / self.train_batch_size                          # :686
+        wl_a = weighted_loss_a.sum() / self.train_batch_size                          # :687
+        accelerate_backward(wl_x, self.grad_accum_steps, retain_graph=retain_graph)   # :691
+        grads_x = {n: p.grad.clone() for n, p in self.model.named_parameters()}       # :693-696
+        accelerate_backward(wl_a, self.grad_accum_steps)                              # :702
+        for n, p in self.model.named_parameters():                                    # :705-711
+            true_grad = p.grad.clone() - grads_x[n]
+            if n not in self.accum_loss_a:
+                self.accum_loss_a[n] = true_grad
+            else:
+                self.accum_loss_a[n] += true_grad
+
+    def sync_step(self, single_loss: bool, loss_fn: str = "importance_sampling_with_mixture",
+                  scaling_norm: Optional[float] = None, eta: Optional[float] = None, max_norm: float = 1.0,
+                  inf_guard: bool = False) -> Dict[str, Tensor]:
+        out: Dict[str, Tensor] = {}
+        if not single_loss:
+            for n, p in self.model.named_parameters():                                # :717-718
+                self.accum_loss_x[n] = p.grad.clone() - self.accum_loss_a[n]
+            sq_x = 0.0
+            sq_a = 0.0
+            for g in self.accum_loss_x.values():                                      # :725-726
+                sq_x = sq_x + torch.norm(g, p=2) ** 2
+            for g in self.accum_loss_a.values():                                      # :729-730
+                sq_a = sq_a + torch.norm(g, p=2) ** 2
+            norm_x = torch.sqrt(sq_x)                                                 # :733-734
+            norm_a = torch.sqrt(sq_a)
+            if loss_fn == "erasediff":                                                # :740-742
+                dot = sum(torch.sum(self.accum_loss_x[n] * self.accum_loss_a[n])
+                          for n, _ in self.model.named_parameters())
+                scaling_factor = eta - dot / (norm_a ** 2)
+                scaling_factor = -max(scaling_factor, 0)
+            else:                                                                     # :746
+                scaling_factor = scaling_norm / norm_a
+                if inf_guard and torch.isinf(scaling_factor):                         # delete_tshirt.py:688-690
+                    scaling_factor = 0
+            for n, p in self.model.named_parameters():                                # :749-750
+                p.grad = self.accum_loss_x[n] - scaling_factor * self.accum_loss_a[n]
+            out.update(norm_x=norm_x, norm_a=norm_a, scaling_factor=torch.as_tensor(scaling_factor))
+            self.accum_loss_x, self.accum_loss_a = {}, {}
+        if max_norm is not None:
+            out["total_norm"] = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm)  # :767
+        return out
+
+
+def combine_flat(g_x: Tensor, g_a: Tensor, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
+                 max_norm: Optional[float] = 1.0, inf_guard: bool = False):
+    """The sync-step arithmetic of ``ReferenceGradLoop.sync_step`` on ONE flat tensor pair (what the
+    combine amounts to when the model has a single parameter tensor). Returns
+    (grad, norm_x, norm_a, scaling_factor, total_norm, clip_coef)."""
+    norm_x = torch.sqrt(torch.norm(g_x, p=2) ** 2)
+    norm_a = torch.sqrt(torch.norm(g_a, p=2) ** 2)
+    if eta is not None:
+        s = eta - torch.sum(g_x * g_a) / (norm_a ** 2)
+        s = -max(s, 0)
+    elif scaling_norm is not None:
+        s = scaling_norm / norm_a
+        if inf_guard and torch.isinf(s):
+            s = 0
+    else:
+        s = 0
+    grad = g_x - s * g_a
+    total_norm = torch.norm(grad, p=2)
+    clip = torch.ones((), dtype=grad.dtype)
+    if max_norm is not None:
+        clip = torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)
+        grad = grad * clip
+    return grad, norm_x, norm_a, torch.as_tensor(s, dtype=grad.dtype), total_norm, clip
+
+
+# --------------------------------------------------------------------------------------------------
+# Per-batch statistics (delete_celeb.py:626-656) — consumed by the stats tests
+# --------------------------------------------------------------------------------------------------
+def batch_stats(items: Sequence[Optional[Tensor]]) -> Dict[str, float]:
+    loss, loss_x, loss_a, w_x, w_a, _wlx, _wla = items
+    stats: Dict[str, float] = {}
+    for name, t in (("loss", loss), ("loss_x", loss_x), ("loss_a", loss_a)):
+        if t is not None:
+            per = t.mean(dim=list(range(1, t.dim())))
+            stats[f"{name}/mean"] = t.mean().item()
+            stats[f"{name}/max"] = per.max().item()
+            stats[f"{name}/min"] = per.min().item()
+            stats[f"{name}/std"] = per.std().item()
+    for name, t in (("importance_weight_x", w_x), ("importance_weight_a", w_a)):
+        if t is not None:
+            stats[f"{name}/mean"] = t.mean().item()
+            stats[f"{name}/max"] = t.max().item()
+            stats[f"{name}/min"] = t.min().item()
+            stats[f"{name}/std"] = t.std().item()
+    return stats
+
+
+class StubUNet(torch.nn.Module):
+    """UNet stand-in for oracle/kernel parity and for timing the path without the UNet masking it
+    (BASELINE.md §4): one scale parameter and one bias, honouring the call convention
+    ``unet(x, t, **conditioning, return_dict=False)[0]`` (ddpm_deletion_loss.py:24)."""
+
+    def __init__(self, init_scale: float = 0.75, init_bias: float = 0.05, dtype=torch.float32):
+        super().__init__()
+        self.scale = torch.nn.Parameter(torch.tensor(init_scale, dtype=dtype))
+        self.bias = torch.nn.Parameter(torch.tensor(init_bias, dtype=dtype))
+
+    def forward(self, x, timesteps, encoder_hidden_states=None, return_dict=False, **kw):
+        out = x.to(self.scale.dtype) * self.scale + self.bias
+        if encoder_hidden_states is not None:
+            out = out + encoder_hidden_states.to(out.dtype).mean() * 0.01
+        return (out,)

@@ -1,0 +1,12 @@
+"""siss_b200 — B200-native (sm_100a) kernels for the SISS data-unlearning hot path.
+
+Host side mirrors the reference's interface for this path:
+  * ``siss_b200.losses.DDPMDeletionLoss``      — losses/ddpm_deletion_loss.py
+  * ``siss_b200.scheduler.SissDDPMScheduler``  — the DDPMScheduler surface the tasks use (add_noise)
+  * ``siss_b200.grad_combine.GradCombiner``    — the inline two-term gradient combine of delete_*.py
+  * ``siss_b200.step.UnlearnStep``             — the fused fast path (nothing [B,D]-sized materialised)
+All compute goes through libsiss_b200.so (C ABI in include/siss_b200.h). No CPU fallback.
+"""
+from ._lib import SissLibraryError  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,97 @@
+"""ctypes binding of libsiss_b200.so (the C ABI declared in include/siss_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing or the device is not a B200
+(sm_100), every entry point raises. The CPU restatement of the algorithm lives under ``oracle/``
+and is test infrastructure only.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, POINTER
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libsiss_b200.so"
+
+SISS_F32, SISS_BF16, SISS_F16 = 0, 1, 2
+SISS_COMBINE_SCALING_NORM, SISS_COMBINE_ERASEDIFF, SISS_COMBINE_NONE = 0, 1, 2
+ABI_VERSION = 1
+
+
+class SissLibraryError(RuntimeError):
+    """libsiss_b200.so is missing, stale, or returned an error code."""
+
+
+# name -> (restype, argtypes); mirrors include/siss_b200.h one to one
+_P, _I, _L, _F, _D = c_void_p, c_int, c_int64, c_float, c_double
+SIGNATURES = {
+    "siss_abi_version": (_I, []),
+    "siss_error_string": (c_char_p, [_I]),
+    "siss_check_device": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "siss_add_noise": (_I, [_P, _P, _P, _P, _I, _P, _L, _L, _I, _P]),
+    "siss_add_noise_pair": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _L, _L, _I, _P]),
+    "siss_row_workspace_bytes": (_L, [_L]),
+    "siss_mixture_weights": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "siss_add_noise_mixture": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "siss_wmse_fwd_bwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _L, _L, _P]),
+    "siss_wmse_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
+    "siss_wmse_bwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P,
+                           _P, _I, _P, _I, _P, _I, _P, _I, _P, _L, _L, _P]),
+    "siss_sqerr_fwd": (_I, [_P, _I, _P, _I, _P, _P, _F, _L, _P]),
+    "siss_sqerr_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _F, _I, _P, _L, _P]),
+    "siss_dual_mse_fwd_bwd": (_I, [_P, _P, _I, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _L, _L, _P]),
+    "siss_norm3_workspace_bytes": (_L, []),
+    "siss_norm3": (_I, [_P, _P, _L, _P, _P, _P]),
+    "siss_combine": (_I, [_P, _P, _P, _L, _P, _I, _F, _F, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; raise SissLibraryError if it is absent or from another ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SissLibraryError(
+            f"{LIB_PATH} not found. Build it with `python -m siss_b200.build` "
+            "(or __graft_entry__.build()). siss_b200 has no CPU or PyTorch fallback."
+        )
+    try:
+        lib = ctypes.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover - depends on the environment
+        raise SissLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise SissLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.siss_abi_version()
+    if got != ABI_VERSION:
+        raise SissLibraryError(f"{LIB_PATH} has ABI version {got}, python layer expects {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def error_string(code: int) -> str:
+    return load().siss_error_string(code).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise SissLibraryError(f"{what} failed with code {code}: {error_string(code)}")
+
+
+_device_checked = False
+
+
+def require_b200() -> None:
+    """Raise unless the current CUDA device is sm_100. Called once by the first op."""
+    global _device_checked
+    if _device_checked:
+        return
+    sm, major, minor = c_int(), c_int(), c_int()
+    check(load().siss_check_device(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "siss_check_device")
+    _device_checked = True

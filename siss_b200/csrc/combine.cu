@@ -1,0 +1,255 @@
+// K4: the two-term gradient combine on flat fp32 gradient buffers.
+//   K4a siss_norm3   : { sum g_x^2, sum g_a^2, sum g_x g_a }  (8 B/param)
+//   K4b siss_combine : out = clip * (g_x - s * g_a)            (12 B/param)
+// Reference: delete_celeb.py:714-753 (+ delete_tshirt.py:688-690 inf guard) and the
+// clip_grad_norm_(1.0) at delete_celeb.py:767. See include/siss_b200.h.
+//
+// Both are persistent grid-stride streaming kernels (grid = SMs x resident CTAs). K4b walks the
+// buffers in the opposite direction to K4a so that the tail K4a left in the 126 MB L2 is the
+// first thing K4b reads. The three scalars travel from K4a to K4b through device memory: no host
+// synchronisation between them (an NCCL all-reduce of the three doubles can sit in between).
+
+#include "common.cuh"
+
+namespace siss {
+
+int cached_sm_count();
+
+constexpr int kK4Occ = 4;     // resident CTAs per SM the kernels are compiled for
+constexpr int kK4Unroll = 4;  // float4 per stream per thread per iteration
+constexpr long long kK4Chunk = (long long)kThreads * kK4Unroll;  // float4 per CTA iteration
+
+struct Norm3Workspace {
+    unsigned int* counter;  // 1 ticket counter, zero between launches
+    double* partials;       // [grid][3]
+};
+
+constexpr int kMaxNormGrid = 148 * 8;
+
+inline Norm3Workspace carve_norm3(void* ws) {
+    Norm3Workspace w;
+    w.counter = reinterpret_cast<unsigned int*>(ws);
+    w.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+    return w;
+}
+
+__global__ void __launch_bounds__(kThreads, kK4Occ)
+norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long long n, long long nvec,
+             double* __restrict__ sums3, Norm3Workspace ws) {
+    __shared__ double red[3 * kWarps];
+    __shared__ int flag;
+    double acc[3] = {0.0, 0.0, 0.0};
+
+    const long long nchunks = (nvec + kK4Chunk - 1) / kK4Chunk;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const long long base = c * kK4Chunk + threadIdx.x;
+        uint4 rx[kK4Unroll], ra[kK4Unroll];
+        bool ok[kK4Unroll];
+#pragma unroll
+        for (int j = 0; j < kK4Unroll; ++j) {
+            const long long i = base + (long long)j * kThreads;
+            ok[j] = i < nvec;
+            if (ok[j]) {
+                rx[j] = ldg_stream(gx + 4 * i);
+                ra[j] = ldg_stream(ga + 4 * i);
+            }
+        }
+        // fp32 products, fp32 sum over the <=16 elements of this iteration, fp64 across iterations
+        float sxx = 0.f, saa = 0.f, sxa = 0.f;
+#pragma unroll
+        for (int j = 0; j < kK4Unroll; ++j) {
+            if (!ok[j]) continue;
+            float x[4], a[4];
+            VecTraits<float>::unpack(rx[j], x);
+            VecTraits<float>::unpack(ra[j], a);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sxx = fmaf(x[q], x[q], sxx);
+                saa = fmaf(a[q], a[q], saa);
+                sxa = fmaf(x[q], a[q], sxa);
+            }
+        }
+        acc[0] += (double)sxx; acc[1] += (double)saa; acc[2] += (double)sxa;
+    }
+    // scalar remainder (n % 4 elements, or everything when the buffers are not 16B aligned)
+    {
+        const long long start = nvec * 4;
+        const long long stride = (long long)gridDim.x * kThreads;
+        for (long long i = start + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+            const float x = gx[i], a = ga[i];
+            acc[0] += (double)(x * x); acc[1] += (double)(a * a); acc[2] += (double)(x * a);
+        }
+    }
+
+    block_sum<3>(acc, red);
+    if (threadIdx.x == 0) {
+        ws.partials[3 * blockIdx.x + 0] = acc[0];
+        ws.partials[3 * blockIdx.x + 1] = acc[1];
+        ws.partials[3 * blockIdx.x + 2] = acc[2];
+    }
+    if (last_cta_ticket(ws.counter, gridDim.x, &flag)) {
+        // fixed-order final reduce by warp 0: lane l sums partials l, l+32, ... then butterfly
+        if (threadIdx.x < 32) {
+            double t[3] = {0.0, 0.0, 0.0};
+            const volatile double* p = ws.partials;
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) {
+                t[0] += p[3 * b + 0]; t[1] += p[3 * b + 1]; t[2] += p[3 * b + 2];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] = warp_sum(t[k]);
+            if (threadIdx.x == 0) { sums3[0] = t[0]; sums3[1] = t[1]; sums3[2] = t[2]; }
+        }
+    }
+}
+
+struct CombineScalars {
+    float s;     // scaling factor
+    float clip;  // clip coefficient (<= 1)
+};
+
+// Scalar prologue shared by every thread of K4b; fp32 op order of the reference.
+__device__ __forceinline__ CombineScalars combine_scalars(const double* __restrict__ sums3, int mode, float value,
+                                                          float max_norm, int inf_guard, float* stats5,
+                                                          bool write_stats) {
+    const double sxx = sums3[0], saa = sums3[1], sxa = sums3[2];
+    const float n_x = sqrtf((float)sxx);  // torch.sqrt(sum of per-tensor norm**2), delete_celeb.py:733-734
+    const float n_a = sqrtf((float)saa);
+    float s;
+    if (mode == SISS_COMBINE_NONE) {
+        s = 0.0f;
+    } else if (mode == SISS_COMBINE_ERASEDIFF) {
+        // eta - <g_x,g_a> / ||g_a||**2 ; -max(., 0)      delete_celeb.py:741-742
+        float sf = __fsub_rn(value, __fdiv_rn((float)sxa, __fmul_rn(n_a, n_a)));
+        sf = (0.0f > sf) ? 0.0f : sf;  // python max(sf, 0): keeps NaN
+        s = -sf;
+    } else {
+        s = __fdiv_rn(value, n_a);     // scaling_norm / ||g_a||   delete_celeb.py:746
+        if (inf_guard && isinf(s)) s = 0.0f;  // delete_tshirt.py:688-690
+    }
+    // ||g_x - s g_a||^2 from the three sums, in fp64
+    const double sd = (double)s;
+    double tn2 = sxx - 2.0 * sd * sxa + sd * sd * saa;
+    if (tn2 < 0.0) tn2 = 0.0;
+    const float tn = (float)sqrt(tn2);
+    float clip = 1.0f;
+    if (max_norm > 0.0f) {
+        // torch.nn.utils.clip_grad_norm_: max_norm / (total_norm + 1e-6), clamped to 1
+        clip = __fdiv_rn(max_norm, __fadd_rn(tn, 1e-6f));
+        clip = (clip > 1.0f) ? 1.0f : clip;
+    }
+    if (write_stats && stats5) {
+        stats5[0] = n_x; stats5[1] = n_a; stats5[2] = s; stats5[3] = tn; stats5[4] = clip;
+    }
+    CombineScalars r; r.s = s; r.clip = clip;
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, kK4Occ)
+combine_kernel(const float* gx, const float* ga, float* out, long long n, long long nvec,
+               const double* __restrict__ sums3, int mode, float value, float max_norm, int inf_guard,
+               float* __restrict__ stats5) {
+    const CombineScalars cs =
+        combine_scalars(sums3, mode, value, max_norm, inf_guard, stats5, blockIdx.x == 0 && threadIdx.x == 0);
+    const float s = cs.s, clip = cs.clip;
+
+    const long long nchunks = (nvec + kK4Chunk - 1) / kK4Chunk;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const long long base = (nchunks - 1 - c) * kK4Chunk + threadIdx.x;  // reverse of K4a's order
+        uint4 rx[kK4Unroll], ra[kK4Unroll];
+        bool ok[kK4Unroll];
+#pragma unroll
+        for (int j = 0; j < kK4Unroll; ++j) {
+            const long long i = base + (long long)j * kThreads;
+            ok[j] = i < nvec;
+            if (ok[j]) {
+                rx[j] = ldg_v4(gx + 4 * i);   // coherent loads: `out` may alias g_x / g_a
+                ra[j] = ldg_v4(ga + 4 * i);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kK4Unroll; ++j) {
+            if (!ok[j]) continue;
+            const long long i = base + (long long)j * kThreads;
+            float x[4], a[4], o[4];
+            VecTraits<float>::unpack(rx[j], x);
+            VecTraits<float>::unpack(ra[j], a);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                o[q] = __fmul_rn(__fsub_rn(x[q], __fmul_rn(s, a[q])), clip);  // mul, sub, then clip's mul_
+            stg_stream(out + 4 * i, VecTraits<float>::pack(o));
+        }
+    }
+    {
+        const long long start = nvec * 4;
+        const long long stride = (long long)gridDim.x * kThreads;
+        for (long long i = start + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+            out[i] = __fmul_rn(__fsub_rn(gx[i], __fmul_rn(s, ga[i])), clip);
+    }
+}
+
+static int k4_grid(long long nvec, long long n) {
+    long long work = (nvec + kK4Chunk - 1) / kK4Chunk;
+    if (nvec * 4 < n) {
+        const long long tail_blocks = (n - nvec * 4 + kThreads - 1) / kThreads;
+        if (tail_blocks > work) work = tail_blocks;
+    }
+    long long grid = (long long)cached_sm_count() * kK4Occ;
+    if (grid > kMaxNormGrid) grid = kMaxNormGrid;
+    if (work < grid) grid = work;
+    if (grid < 1) grid = 1;
+    return (int)grid;
+}
+
+}  // namespace siss
+
+using namespace siss;
+
+extern "C" {
+
+int64_t siss_norm3_workspace_bytes(void) { return 256 + (int64_t)kMaxNormGrid * 3 * (int64_t)sizeof(double); }
+
+int siss_norm3(const float* g_x, const float* g_a, int64_t n, double* sums3, void* workspace,
+               siss_stream_t stream) {
+    if (!g_x || !g_a || !sums3 || !workspace || n < 0) return SISS_EINVAL;
+    const long long nvec = (aligned16(g_x) && aligned16(g_a)) ? n / 4 : 0;
+    Norm3Workspace ws = carve_norm3(workspace);
+    norm3_kernel<<<k4_grid(nvec, n), kThreads, 0, (cudaStream_t)stream>>>(g_x, g_a, n, nvec, sums3, ws);
+    return (int)cudaGetLastError();
+}
+
+int siss_combine(const float* g_x, const float* g_a, float* out, int64_t n, const double* sums3,
+                 int mode, float value, float max_norm, int inf_guard, float* stats5, siss_stream_t stream) {
+    if (!g_x || !g_a || !out || !sums3 || n < 0) return SISS_EINVAL;
+    if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_NONE) return SISS_EINVAL;
+    const long long nvec = (aligned16(g_x) && aligned16(g_a) && aligned16(out)) ? n / 4 : 0;
+    combine_kernel<<<k4_grid(nvec, n), kThreads, 0, (cudaStream_t)stream>>>(
+        g_x, g_a, out, n, nvec, sums3, mode, value, max_norm, inf_guard, stats5);
+    return (int)cudaGetLastError();
+}
+
+int siss_abi_version(void) { return SISS_B200_ABI_VERSION; }
+
+const char* siss_error_string(int code) {
+    switch (code) {
+        case SISS_OK: return "ok";
+        case SISS_EINVAL: return "siss: invalid argument (null pointer, negative size or bad enum)";
+        case SISS_EUNSUPPORTED: return "siss: dtype combination not compiled into libsiss_b200";
+        case SISS_EARCH: return "siss: device is not sm_100 (B200); this library has no other target";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "siss: unknown error";
+    }
+}
+
+int siss_check_device(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0, major = 0, minor = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if (sm_count) *sm_count = sms;
+    if (cc_major) *cc_major = major;
+    if (cc_minor) *cc_minor = minor;
+    return major == 10 ? SISS_OK : SISS_EARCH;
+}
+
+}  // extern "C"

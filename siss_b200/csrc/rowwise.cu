@@ -1,0 +1,321 @@
+// K1 (DDPM add_noise), K2 (defensive mixture + importance weights) and the fused K1 o K2.
+// See include/siss_b200.h for the reference call sites each entry point replaces.
+//
+// HBM traffic (s = sizeof(T)):  K1 single 3s, K1 pair 5s, K2 4s, K1oK2 4s bytes per element.
+// All three are pure streaming kernels: 128-bit coalesced loads issued in a batch per iteration,
+// fp32 math in registers, 128-bit stores. K2 additionally reduces three sums per row with
+// warp shuffles -> smem -> fixed-order cross-CTA combine.
+
+#include "rowtile.cuh"
+
+namespace siss {
+
+int cached_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = kNumSMsB200;
+    }
+    return sms;
+}
+
+// sqrt(abar_t) and sqrt(1 - abar_t) the way diffusers 0.27.2 DDPMScheduler.add_noise forms them:
+// the table is cast to the sample dtype first, and each op result is rounded to that dtype.
+template <typename T>
+__device__ __forceinline__ void noise_coeffs(const float* __restrict__ ac, int t, float& sa, float& s1) {
+    using VT = VecTraits<T>;
+    const float a = VT::round(ac[t]);
+    sa = VT::round(sqrtf(a));
+    s1 = VT::round(sqrtf(VT::round(__fsub_rn(1.0f, a))));
+}
+
+// x_t element: round(round(sa*x) + round(s1*n)); __f*_rn blocks FMA contraction so the fp32 path
+// is bit-identical to eager's mul, mul, add.
+template <typename T>
+__device__ __forceinline__ float noised(float sa, float s1, float x, float n) {
+    using VT = VecTraits<T>;
+    return VT::round(__fadd_rn(VT::round(__fmul_rn(sa, x)), VT::round(__fmul_rn(s1, n))));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------
+constexpr int kK1Vpt = 2;
+constexpr int kK1Occ = 4;
+
+template <typename T, int W, int NSRC>
+__global__ void __launch_bounds__(kThreads, kK1Occ)
+add_noise_kernel(const T* __restrict__ x0, const T* __restrict__ a0, const T* __restrict__ noise,
+                 const int64_t* __restrict__ ts, const float* __restrict__ ac, int T_steps,
+                 T* __restrict__ xt_x, T* __restrict__ xt_a, RowTiling rt) {
+    constexpr int VPT = kK1Vpt;
+    const long long step = (long long)kThreads * VPT;
+    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
+        const long long row = tile / rt.nch;
+        const int ch = (int)(tile - row * rt.nch);
+        float sa, s1;
+        noise_coeffs<T>(ac, wrap_timestep(ts[row], T_steps), sa, s1);
+        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
+        for (int it = 0; it < rt.iters; ++it) {
+            RawUnit<T, W> rx[VPT], ra[VPT], rn[VPT];
+            long long e[VPT];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                const long long u = ubase + it * step + (long long)j * kThreads;
+                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                if (e[j] >= 0) {
+                    fetch_raw<T, W>(x0 + e[j], rx[j]);
+                    if (NSRC == 2) fetch_raw<T, W>(a0 + e[j], ra[j]);
+                    fetch_raw<T, W>(noise + e[j], rn[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                if (e[j] < 0) continue;
+                float x[W], n[W], o[W];
+                decode_raw<T, W>(rx[j], x);
+                decode_raw<T, W>(rn[j], n);
+#pragma unroll
+                for (int k = 0; k < W; ++k) o[k] = noised<T>(sa, s1, x[k], n[k]);
+                store_unit<T, W>(xt_x + e[j], o);
+                if (NSRC == 2) {
+                    decode_raw<T, W>(ra[j], x);
+#pragma unroll
+                    for (int k = 0; k < W; ++k) o[k] = noised<T>(sa, s1, x[k], n[k]);
+                    store_unit<T, W>(xt_a + e[j], o);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int NSRC>
+static int launch_add_noise(const void* x0, const void* a0, const void* noise, const int64_t* ts,
+                            const float* ac, int T_steps, void* xt_x, void* xt_a,
+                            long long B, long long D, cudaStream_t st) {
+    constexpr int N = VecTraits<T>::N;
+    bool vec = (D % N == 0) && aligned16(x0) && aligned16(noise) && aligned16(xt_x);
+    if (NSRC == 2) vec = vec && aligned16(a0) && aligned16(xt_a);
+    if (vec) {
+        RowTiling rt = make_row_tiling(B, D, N, kK1Vpt, kK1Occ);
+        add_noise_kernel<T, N, NSRC><<<rt.grid, kThreads, 0, st>>>(
+            (const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a, rt);
+    } else {
+        RowTiling rt = make_row_tiling(B, D, 1, kK1Vpt, kK1Occ);
+        add_noise_kernel<T, 1, NSRC><<<rt.grid, kThreads, 0, st>>>(
+            (const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a, rt);
+    }
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 and K1 o K2
+// ---------------------------------------------------------------------------------------------
+constexpr int kK2Vpt = 2;
+constexpr int kK2Occ = 4;
+
+// Row epilogue (one thread): losses/ddpm_deletion_loss.py:34,38 (division by 2 sigma^2) and
+// :41-45 (ratios and weights), in the reference's fp32 op order. `sd` is the directly
+// accumulated sum of (r_x^2 - r_a^2), so delta = dist_x - dist_a without the cancellation.
+__device__ __forceinline__ void finalize_row_weights(double sx, double sa, double sd, float sigma,
+                                                     float lam, float one_m_lam, long long row,
+                                                     float* __restrict__ dist_x, float* __restrict__ dist_a,
+                                                     float* __restrict__ w_x, float* __restrict__ w_a) {
+    const float two_s2 = __fmul_rn(2.0f, __fmul_rn(sigma, sigma));
+    const float dx = __fdiv_rn((float)sx, two_s2);
+    const float da = __fdiv_rn((float)sa, two_s2);
+    const float delta = __fdiv_rn((float)sd, two_s2);
+    const float r_ax = expf(delta);    // ratio_a_x = exp(dist_x - dist_a)
+    const float r_xa = expf(-delta);   // ratio_x_a = exp(dist_a - dist_x)
+    dist_x[row] = dx;
+    dist_a[row] = da;
+    w_x[row] = __fdiv_rn(1.0f, __fadd_rn(one_m_lam, __fmul_rn(lam, r_ax)));
+    w_a[row] = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(one_m_lam, r_xa), lam));
+}
+
+template <typename T, int W, bool FUSED_NOISE>
+__global__ void __launch_bounds__(kThreads, kK2Occ)
+mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      FUSED: unused
+               const T* __restrict__ src_a,   // !FUSED: noisy forget batch    FUSED: unused
+               const T* __restrict__ x0, const T* __restrict__ a0,
+               const T* __restrict__ noise,   // FUSED only
+               const uint8_t* __restrict__ keep, const int64_t* __restrict__ ts,
+               const float* __restrict__ ac,  // FUSED only
+               const float* __restrict__ gamma, const float* __restrict__ sigma, int T_steps,
+               float lam, float one_m_lam,
+               T* __restrict__ x_mix, float* __restrict__ dist_x, float* __restrict__ dist_a,
+               float* __restrict__ w_x, float* __restrict__ w_a,
+               RowWorkspace ws, RowTiling rt) {
+    constexpr int VPT = kK2Vpt;
+    __shared__ float red[3 * kWarps];
+    __shared__ int flag;
+    const long long step = (long long)kThreads * VPT;
+
+    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
+        const long long row = tile / rt.nch;
+        const int ch = (int)(tile - row * rt.nch);
+        const int t = wrap_timestep(ts[row], T_steps);
+        const bool k = keep[row] != 0;
+        const float g = gamma[t];
+        float sa = 0.f, s1 = 0.f;
+        if (FUSED_NOISE) noise_coeffs<T>(ac, t, sa, s1);
+        const T* __restrict__ sel = FUSED_NOISE ? (k ? x0 : a0) : (k ? src_x : src_a);
+
+        float acc[3] = {0.f, 0.f, 0.f};  // sum r_x^2, sum r_a^2, sum (r_x^2 - r_a^2)
+        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
+        for (int it = 0; it < rt.iters; ++it) {
+            RawUnit<T, W> rx[VPT], ra[VPT], rs[VPT];
+            long long e[VPT];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                const long long u = ubase + it * step + (long long)j * kThreads;
+                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                if (e[j] >= 0) {
+                    fetch_raw<T, W>(x0 + e[j], rx[j]);
+                    fetch_raw<T, W>(a0 + e[j], ra[j]);
+                    // FUSED: the third stream is eps; otherwise the selected noisy row.
+                    fetch_raw<T, W>((FUSED_NOISE ? noise : sel) + e[j], rs[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                if (e[j] < 0) continue;
+                float x[W], a[W], s[W], m[W];
+                decode_raw<T, W>(rx[j], x);
+                decode_raw<T, W>(ra[j], a);
+                decode_raw<T, W>(rs[j], s);
+#pragma unroll
+                for (int q = 0; q < W; ++q) {
+                    m[q] = FUSED_NOISE ? noised<T>(sa, s1, k ? x[q] : a[q], s[q]) : s[q];
+                    const float r_x = __fsub_rn(m[q], __fmul_rn(g, x[q]));
+                    const float r_a = __fsub_rn(m[q], __fmul_rn(g, a[q]));
+                    acc[0] = fmaf(r_x, r_x, acc[0]);
+                    acc[1] = fmaf(r_a, r_a, acc[1]);
+                    acc[2] = fmaf(r_x - r_a, r_x + r_a, acc[2]);
+                }
+                store_unit<T, W>(x_mix + e[j], m);
+            }
+        }
+
+        block_sum<3>(acc, red);
+        if (rt.nch == 1) {
+            if (threadIdx.x == 0)
+                finalize_row_weights(acc[0], acc[1], acc[2], sigma[t], lam, one_m_lam, row,
+                                     dist_x, dist_a, w_x, w_a);
+        } else {
+            float* slot = ws.partials + (row * kMaxRowChunks + ch) * kRowPartialStride;
+            if (threadIdx.x == 0) { slot[0] = acc[0]; slot[1] = acc[1]; slot[2] = acc[2]; }
+            if (last_cta_ticket(ws.counters + row, (unsigned)rt.nch, &flag)) {
+                if (threadIdx.x == 0) {
+                    double sx = 0.0, sy = 0.0, sd = 0.0;
+                    const volatile float* p = ws.partials + row * kMaxRowChunks * kRowPartialStride;
+                    for (int c = 0; c < rt.nch; ++c) {
+                        sx += (double)p[c * kRowPartialStride + 0];
+                        sy += (double)p[c * kRowPartialStride + 1];
+                        sd += (double)p[c * kRowPartialStride + 2];
+                    }
+                    finalize_row_weights(sx, sy, sd, sigma[t], lam, one_m_lam, row,
+                                         dist_x, dist_a, w_x, w_a);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, bool FUSED>
+static int launch_mixture(const void* src_x, const void* src_a, const void* x0, const void* a0,
+                          const void* noise, const uint8_t* keep, const int64_t* ts, const float* ac,
+                          const float* gamma, const float* sigma, int T_steps, double lambd,
+                          void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
+                          void* workspace, long long B, long long D, cudaStream_t st) {
+    constexpr int N = VecTraits<T>::N;
+    // torch wraps the python scalars `lambd` and `1 - lambd` to the tensor dtype (fp32).
+    const float lam = (float)lambd;
+    const float one_m = (float)(1.0 - lambd);
+    bool vec = (D % N == 0) && aligned16(x0) && aligned16(a0) && aligned16(x_mix);
+    vec = vec && (FUSED ? aligned16(noise) : (aligned16(src_x) && aligned16(src_a)));
+    RowWorkspace ws = carve_row_workspace(workspace, B);
+    if (vec) {
+        RowTiling rt = make_row_tiling(B, D, N, kK2Vpt, kK2Occ);
+        mixture_kernel<T, N, FUSED><<<rt.grid, kThreads, 0, st>>>(
+            (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, rt);
+    } else {
+        RowTiling rt = make_row_tiling(B, D, 1, kK2Vpt, kK2Occ);
+        mixture_kernel<T, 1, FUSED><<<rt.grid, kThreads, 0, st>>>(
+            (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, rt);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace siss
+
+using namespace siss;
+
+#define SISS_DISPATCH_DTYPE(dtype, ...)                                          \
+    switch (dtype) {                                                             \
+        case SISS_F32:  { using T = float;          return __VA_ARGS__; }        \
+        case SISS_BF16: { using T = __nv_bfloat16;  return __VA_ARGS__; }        \
+        case SISS_F16:  { using T = __half;         return __VA_ARGS__; }        \
+        default: return SISS_EUNSUPPORTED;                                       \
+    }
+
+extern "C" {
+
+int64_t siss_row_workspace_bytes(int64_t B) {
+    if (B < 1) B = 1;
+    return row_ws_counter_bytes(B) + B * (int64_t)kMaxRowChunks * kRowPartialStride * (int64_t)sizeof(float);
+}
+
+int siss_add_noise(const void* x0, const void* noise, const int64_t* timesteps,
+                   const float* alphas_cumprod, int T_steps, void* xt,
+                   int64_t B, int64_t D, int dtype, siss_stream_t stream) {
+    if (!x0 || !noise || !timesteps || !alphas_cumprod || !xt || B < 0 || D < 0 || T_steps < 1) return SISS_EINVAL;
+    if (B == 0 || D == 0) return SISS_OK;
+    SISS_DISPATCH_DTYPE(dtype, (launch_add_noise<T, 1>(x0, nullptr, noise, timesteps, alphas_cumprod, T_steps,
+                                                       xt, nullptr, B, D, (cudaStream_t)stream)));
+}
+
+int siss_add_noise_pair(const void* x0, const void* a0, const void* noise, const int64_t* timesteps,
+                        const float* alphas_cumprod, int T_steps, void* xt_x, void* xt_a,
+                        int64_t B, int64_t D, int dtype, siss_stream_t stream) {
+    if (!x0 || !a0 || !noise || !timesteps || !alphas_cumprod || !xt_x || !xt_a || B < 0 || D < 0 || T_steps < 1)
+        return SISS_EINVAL;
+    if (B == 0 || D == 0) return SISS_OK;
+    SISS_DISPATCH_DTYPE(dtype, (launch_add_noise<T, 2>(x0, a0, noise, timesteps, alphas_cumprod, T_steps,
+                                                       xt_x, xt_a, B, D, (cudaStream_t)stream)));
+}
+
+int siss_mixture_weights(const void* xt_x, const void* xt_a, const void* x0, const void* a0,
+                         const uint8_t* keep_mask, const int64_t* timesteps,
+                         const float* gamma, const float* sigma, int T_steps, double lambd,
+                         void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
+                         void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream) {
+    if (!xt_x || !xt_a || !x0 || !a0 || !keep_mask || !timesteps || !gamma || !sigma || !x_mix || !dist_x ||
+        !dist_a || !w_x || !w_a || !workspace || B < 0 || D < 1 || T_steps < 1)
+        return SISS_EINVAL;
+    if (B == 0) return SISS_OK;
+    SISS_DISPATCH_DTYPE(dtype, (launch_mixture<T, false>(xt_x, xt_a, x0, a0, nullptr, keep_mask, timesteps, nullptr,
+                                                         gamma, sigma, T_steps, lambd, x_mix, dist_x, dist_a, w_x,
+                                                         w_a, workspace, B, D, (cudaStream_t)stream)));
+}
+
+int siss_add_noise_mixture(const void* x0, const void* a0, const void* noise,
+                           const uint8_t* keep_mask, const int64_t* timesteps,
+                           const float* alphas_cumprod, const float* gamma, const float* sigma, int T_steps,
+                           double lambd,
+                           void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
+                           void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream) {
+    if (!x0 || !a0 || !noise || !keep_mask || !timesteps || !alphas_cumprod || !gamma || !sigma || !x_mix ||
+        !dist_x || !dist_a || !w_x || !w_a || !workspace || B < 0 || D < 1 || T_steps < 1)
+        return SISS_EINVAL;
+    if (B == 0) return SISS_OK;
+    SISS_DISPATCH_DTYPE(dtype, (launch_mixture<T, true>(nullptr, nullptr, x0, a0, noise, keep_mask, timesteps,
+                                                        alphas_cumprod, gamma, sigma, T_steps, lambd, x_mix, dist_x,
+                                                        dist_a, w_x, w_a, workspace, B, D, (cudaStream_t)stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""Two-term gradient combine (K4) — the function the reference never factored out.
+
+In the reference the logic is inline, three times (delete_celeb.py:682-767, delete_tshirt.py:624-711,
+delete_sd.py:1039-1123):
+
+    backward(weighted_loss_x, retain_graph)          ; clone every param.grad      -> g_x
+    backward(weighted_loss_a)                        ; grad - g_x, += into a dict  -> accum_a
+    at the sync step: accum_x = grad - accum_a ; ||accum_x||, ||accum_a|| ; scaling_factor ;
+                      param.grad = accum_x - scaling_factor * accum_a ; clip_grad_norm_(1.0)
+
+B200 design: two flat fp32 buffers ``G_x`` and ``G_a`` (P parameters each, resident in HBM for the
+whole run). ``param.grad`` is a *view* into one of them; :meth:`begin_x` / :meth:`begin_a` re-point
+the views so autograd itself accumulates the keep term into ``G_x`` and the forget (NegGrad) term
+into ``G_a`` — the reference's per-micro-step clone / subtract / ``+=`` passes (10 P-sized passes and
+~4 launches per parameter tensor) disappear. At the sync step :meth:`combine` runs K4a
+(``siss_norm3``: three sums in one 8 B/param pass) and K4b (``siss_combine``: scale, subtract and the
+folded ``clip_grad_norm_`` in one 12 B/param pass). The scalars stay on the device; nothing here
+synchronises the host.
+
+Data parallel (one process per GPU): samples are independent, so the only exchange is the gradient
+sum. With a process group, :meth:`combine` reduce-scatters ``G_x`` and ``G_a`` (NCCL over NVLink),
+runs K4a on the local 1/N shard, all-reduces the three fp64 scalars the scaling and the clip need,
+runs K4b on the shard and all-gathers the result.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import SISS_COMBINE_ERASEDIFF, SISS_COMBINE_NONE, SISS_COMBINE_SCALING_NORM
+
+_ALIGN = 4  # parameters start on 16-byte boundaries inside the flat buffers
+
+
+class GradCombiner:
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group: Optional[dist.ProcessGroup] = None,
+                 distributed: Optional[bool] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradCombiner needs at least one parameter that requires grad")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise ValueError("GradCombiner expects fp32 parameters (the reference keeps fp32 master weights; "
+                                 "mixed precision is autocast, delete_celeb.py:102-108)")
+            if p.device != dev:
+                raise ValueError("all parameters must live on one device")
+        self.device = dev
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if distributed else 1
+        self.rank = dist.get_rank(process_group) if distributed else 0
+
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.num_params = sum(p.numel() for p in self.params)
+        quantum = _ALIGN * self.world
+        self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's shard is 16B aligned
+        self.g_x = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.g_a = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self._views_x = [self.g_x[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self._views_a = [self.g_a[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self.sums3 = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(5, dtype=torch.float32, device=dev)
+        if self.world > 1:
+            self.shard_len = self.total // self.world
+            self._shard_x = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
+            self._shard_a = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
+        self._dirty_x = False  # G_x holds the previous combined gradient and must be cleared
+        # compute back-ends: the CUDA kernels. (tests of the collective choreography on gloo/CPU
+        # replace these two attributes with the oracle; the product has no other path.)
+        self._norm3 = ops.norm3
+        self._combine = ops.combine
+
+    # ------------------------------------------------------------------------------------------
+    def _point(self, views: List[torch.Tensor]) -> None:
+        for p, v in zip(self.params, views):
+            p.grad = v
+
+    def begin_x(self) -> None:
+        """Call before ``backward(weighted_loss_x)``: gradients now accumulate into ``G_x``."""
+        if self._dirty_x:
+            self.g_x.zero_()
+            self._dirty_x = False
+        self._point(self._views_x)
+
+    def begin_a(self) -> None:
+        """Call between the two backward passes: gradients now accumulate into ``G_a``. This is the
+        whole of delete_celeb.py:693-711 (clone, subtract, accumulate)."""
+        self._point(self._views_a)
+
+    # ------------------------------------------------------------------------------------------
+    def combine(self, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
+                max_norm: Optional[float] = 1.0, inf_guard: bool = False) -> torch.Tensor:
+        """Sync-step combine. Exactly one of ``scaling_norm`` (SISS / No-IS, delete_celeb.py:746) or
+        ``eta`` (EraseDiff, :741-742) must be given. Leaves the result in ``param.grad`` (views of
+        ``G_x``) for ``optimizer.step()`` and returns the device tensor
+        ``[norm_loss_x, norm_loss_a, scaling_factor, total_norm, clip_coef]`` (the first three are the
+        reference's wandb scalars, :748). ``G_a`` is cleared for the next accumulation round."""
+        if (scaling_norm is None) == (eta is None):
+            raise ValueError("give exactly one of scaling_norm= or eta=")
+        mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF
+        value = float(scaling_norm if eta is None else eta)
+        mn = 0.0 if max_norm is None else float(max_norm)
+        if self.world == 1:
+            self._norm3(self.g_x, self.g_a, out=self.sums3)
+            self._combine(self.g_x, self.g_a, self.sums3, mode, value, mn, inf_guard, out=self.g_x, stats=self.stats)
+        else:
+            dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+            dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
+            self._norm3(self._shard_x, self._shard_a, out=self.sums3)
+            dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)  # the scalar-norm all-reduce
+            self._combine(self._shard_x, self._shard_a, self.sums3, mode, value, mn, inf_guard, out=self._shard_x,
+                          stats=self.stats)
+            dist.all_gather_into_tensor(self.g_x, self._shard_x, group=self.group)
+        self.g_a.zero_()
+        self._dirty_x = True
+        self._point(self._views_x)
+        return self.stats
+
+    def clip_only(self, max_norm: float = 1.0) -> torch.Tensor:
+        """Single-term methods (naive_del / simple_neg_del: ``loss is not None``, delete_celeb.py:682-684):
+        gradients are in ``G_x``; only the data-parallel sum and ``clip_grad_norm_`` apply."""
+        if self.world == 1:
+            self._norm3(self.g_x, self.g_x, out=self.sums3)
+            self._combine(self.g_x, self.g_x, self.sums3, SISS_COMBINE_NONE, 0.0, float(max_norm), False,
+                          out=self.g_x, stats=self.stats)
+        else:
+            dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+            self._norm3(self._shard_x, self._shard_x, out=self.sums3)
+            dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)
+            self._combine(self._shard_x, self._shard_x, self.sums3, SISS_COMBINE_NONE, 0.0, float(max_norm),
+                          False, out=self._shard_x, stats=self.stats)
+            dist.all_gather_into_tensor(self.g_x, self._shard_x, group=self.group)
+        self._dirty_x = True
+        self._point(self._views_x)
+        return self.stats
+
+    # ------------------------------------------------------------------------------------------
+    def stats_dict(self) -> Dict[str, float]:
+        """Host copy of the last combine's scalars (this DOES synchronise; call it when logging)."""
+        v = self.stats.tolist()
+        return {"gradient/norm_loss_x": v[0], "gradient/norm_loss_a": v[1], "gradient/scaling_factor": v[2],
+                "gradient/total_norm": v[3], "gradient/clip_coef": v[4]}

@@ -1,0 +1,167 @@
+"""Fused fast path for one unlearning micro-step / optimiser step.
+
+The drop-in class (:mod:`siss_b200.losses`) has to materialise the four ``[B,C,H,W]`` loss tensors
+the reference's 7-tuple promises. A caller that owns its training loop does not need them: per
+micro-step this driver launches
+
+    K1oK2  siss_add_noise_mixture   x0, a0, eps -> x_mix, w_x, w_a                 (4 s B/elem)
+           unet(x_mix, t, **conditioning)                                          (diffusers / any callable)
+    K3     siss_wmse_fwd_bwd        eps_hat, x_mix, x0, a0 -> dL_x/deps_hat, dL_a/deps_hat, row sums
+    autograd.backward(eps_hat, dL_x) into G_x ; autograd.backward(eps_hat, dL_a) into G_a
+
+and per optimiser step K4a + K4b (:class:`siss_b200.grad_combine.GradCombiner`). It reproduces the
+reference loop delete_celeb.py:580-767 (noise is drawn by the caller, as there) including the
+``/ train_batch_size`` and ``/ gradient_accumulation_steps`` scalings, and returns only device tensors:
+nothing here synchronises the host (the reference does ~20 ``.item()`` per micro-step, :626-663).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .grad_combine import GradCombiner
+from .losses.ddpm_deletion_loss import _draw_keep_mask
+from .scheduler import SissDDPMScheduler
+
+TWO_TERM = ("importance_sampling_with_mixture", "double_forward_with_neg_del", "erasediff")
+ONE_TERM = ("naive_del", "simple_neg_del")
+
+
+def upstream_scale(train_batch_size: int, grad_accum_steps: int) -> float:
+    """d(total)/d(weighted_loss element) exactly as autograd forms it for
+    ``(w.sum() / train_batch_size / G).backward()``: fp32(fp32(1/G) / train_batch_size)."""
+    g = np.float32(1.0) / np.float32(grad_accum_steps)
+    return float(np.float32(g) / np.float32(train_batch_size))
+
+
+class UnlearnStep:
+    """One rank's unlearning step. ``train_batch_size`` is the GLOBAL per-micro-step batch the loss is
+    normalised by (``cfg.train_batch_size`` in the reference; under data parallel every rank passes its
+    shard of the batch and the same global value)."""
+
+    def __init__(self, unet: Callable, scheduler: SissDDPMScheduler, combiner: GradCombiner, *,
+                 loss_fn: str = "importance_sampling_with_mixture", train_batch_size: int,
+                 gradient_accumulation_steps: int = 1, lambd: Optional[float] = None,
+                 superfactor: Optional[float] = None, scaling_norm: Optional[float] = None,
+                 eta: Optional[float] = None, max_norm: Optional[float] = 1.0, inf_guard: bool = False):
+        if loss_fn not in TWO_TERM + ONE_TERM:
+            raise ValueError(f"unknown loss_fn {loss_fn!r}")
+        if loss_fn == "importance_sampling_with_mixture" and lambd is None:
+            raise ValueError("importance_sampling_with_mixture needs lambd")
+        if loss_fn == "simple_neg_del" and superfactor is None:
+            raise ValueError("simple_neg_del needs superfactor")
+        if loss_fn == "erasediff" and eta is None:
+            raise ValueError("erasediff needs eta")
+        if loss_fn in ("importance_sampling_with_mixture", "double_forward_with_neg_del") and scaling_norm is None:
+            raise ValueError(f"{loss_fn} needs scaling_norm")
+        self.unet, self.scheduler, self.combiner = unet, scheduler, combiner
+        self.loss_fn = loss_fn
+        self.train_batch_size = int(train_batch_size)
+        self.G = int(gradient_accumulation_steps)
+        self.lambd, self.superfactor = lambd, superfactor
+        self.scaling_norm, self.eta, self.max_norm, self.inf_guard = scaling_norm, eta, max_norm, inf_guard
+        self.go = upstream_scale(self.train_batch_size, self.G)
+        dev = combiner.device
+        self.alphas_cumprod = scheduler.alphas_cumprod.to(dev)
+        self.gamma, self.sigma = scheduler.gamma_sigma(dev)
+        self._micro = 0
+
+    # ------------------------------------------------------------------------------------------
+    def micro_step(self, x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
+                   conditioning: Optional[dict] = None, keep_mask: Optional[torch.Tensor] = None
+                   ) -> Dict[str, torch.Tensor]:
+        """Forward + both backward passes for one micro-batch. Returns per-sample device tensors:
+        ``row_loss_x`` / ``row_loss_a`` (sum over C,H,W of the unweighted squared errors) and, for SISS,
+        ``w_x`` / ``w_a`` / ``dist_x`` / ``dist_a``."""
+        cond = conditioning or {}
+        out: Dict[str, torch.Tensor] = {}
+        cb = self.combiner
+        if self.loss_fn == "importance_sampling_with_mixture":
+            keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
+            x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
+                                                              self.gamma, self.sigma, self.lambd)
+            pred = self.unet(x_mix, timesteps, **cond, return_dict=False)[0]
+            g_x, g_a, rl_x, rl_a = ops.wmse_fwd_bwd(pred.detach(), x_mix, x0, a0, timesteps, self.gamma, self.sigma,
+                                                    w_x, w_a, self.go, self.go)
+            cb.begin_x()
+            torch.autograd.backward(pred, g_x, retain_graph=True)
+            cb.begin_a()
+            torch.autograd.backward(pred, g_a)
+            out.update(w_x=w_x, w_a=w_a, dist_x=d_x, dist_a=d_a, row_loss_x=rl_x, row_loss_a=rl_a)
+        elif self.loss_fn in ("double_forward_with_neg_del", "erasediff"):
+            xt_x, xt_a = self.scheduler.add_noise_pair(x0, a0, noise, timesteps)
+            pred_x = self.unet(xt_x, timesteps, **cond, return_dict=False)[0]
+            pred_a = self.unet(xt_a, timesteps, **cond, return_dict=False)[0]
+            # EraseDiff's forget target: uniform noise drawn after the second forward (ddpm_deletion_loss.py:75)
+            tgt_a = torch.rand_like(pred_a) if self.loss_fn == "erasediff" else noise
+            tgt_x = noise
+            if tgt_a.dtype != tgt_x.dtype:
+                tgt_x = tgt_x.to(tgt_a.dtype)
+            g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a,
+                                                        self.go, self.go)
+            cb.begin_x()
+            torch.autograd.backward(pred_x, g_x)
+            cb.begin_a()
+            torch.autograd.backward(pred_a, g_a)
+            out.update(row_loss_x=rl_x, row_loss_a=rl_a)
+        else:
+            # single-term methods: one forward, one backward, no combine (delete_celeb.py:682-684)
+            if self.loss_fn == "naive_del":
+                xt = self.scheduler.add_noise(x0, noise, timesteps)
+                alpha = 1.0
+            else:
+                xt = self.scheduler.add_noise(a0, noise, timesteps)
+                alpha = -float(self.superfactor)
+            pred = self.unet(xt, timesteps, **cond, return_dict=False)[0]
+            # grad = (go * alpha) * 2 (pred - eps): dual kernel with the second term switched off
+            g, _unused, rl, _ = ops.dual_mse_fwd_bwd(pred.detach(), pred.detach(), noise, noise,
+                                                     float(np.float32(self.go) * np.float32(alpha)), 0.0)
+            cb.begin_x()
+            torch.autograd.backward(pred, g)
+            out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl
+        self._micro += 1
+        return out
+
+    def sync_step(self) -> torch.Tensor:
+        """Gradient combine + clip at the accumulation boundary (delete_celeb.py:714-767). Leaves
+        ``param.grad`` ready for ``optimizer.step()``; returns the device stats tensor
+        ``[norm_loss_x, norm_loss_a, scaling_factor, total_norm, clip_coef]``."""
+        self._micro = 0
+        if self.loss_fn in ONE_TERM:
+            return self.combiner.clip_only(self.max_norm if self.max_norm is not None else 0.0)
+        if self.loss_fn == "erasediff":
+            return self.combiner.combine(eta=self.eta, max_norm=self.max_norm, inf_guard=self.inf_guard)
+        return self.combiner.combine(scaling_norm=self.scaling_norm, max_norm=self.max_norm,
+                                     inf_guard=self.inf_guard)
+
+    @property
+    def is_sync_step(self) -> bool:
+        return self._micro >= self.G
+
+
+def batch_stats(out: Dict[str, torch.Tensor], elems_per_sample: int) -> Dict[str, torch.Tensor]:
+    """The reference's per-batch statistics (delete_celeb.py:626-656) from the O(B) row sums — device
+    scalars, no host sync. mean over all elements == mean of per-sample means (equal row sizes)."""
+    stats: Dict[str, torch.Tensor] = {}
+    for name in ("loss_x", "loss_a"):
+        rows = out.get(f"row_{name}")
+        if rows is None:
+            continue
+        per = rows / elems_per_sample
+        stats[f"{name}/mean"] = per.mean()
+        stats[f"{name}/max"] = per.max()
+        stats[f"{name}/min"] = per.min()
+        stats[f"{name}/std"] = per.std() if per.numel() > 1 else per.new_full((), float("nan"))
+    for name in ("w_x", "w_a"):
+        w = out.get(name)
+        if w is None:
+            continue
+        key = "importance_weight_" + name[-1]
+        stats[f"{key}/mean"] = w.mean()
+        stats[f"{key}/max"] = w.max()
+        stats[f"{key}/min"] = w.min()
+        stats[f"{key}/std"] = w.std() if w.numel() > 1 else w.new_full((), float("nan"))
+    return stats

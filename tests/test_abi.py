@@ -1,0 +1,91 @@
+"""CPU: the C-ABI library loads and exports every symbol include/siss_b200.h declares, the ctypes
+table matches the header arity, and the product path refuses to run without a CUDA device (no
+compute calls are made here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "siss_b200.h").read_text()
+
+
+def declared_functions():
+    src = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    out = {}
+    for m in re.finditer(r"^(?:int|int64_t|const char\*)\s+(siss_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.M | re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        out[m.group(1)] = n
+    return out
+
+
+def test_header_parses():
+    fns = declared_functions()
+    assert len(fns) >= 17
+    for must in ("siss_add_noise_pair", "siss_add_noise_mixture", "siss_mixture_weights", "siss_wmse_fwd_bwd",
+                 "siss_dual_mse_fwd_bwd", "siss_norm3", "siss_combine"):
+        assert must in fns
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from siss_b200 import build, _lib
+    build.build()
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/siss_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from siss_b200 import _lib
+    fns = declared_functions()
+    assert set(_lib.SIGNATURES) == set(fns)
+    for name, nargs in fns.items():
+        assert len(_lib.SIGNATURES[name][1]) == nargs, name
+    lib = _lib.load()
+    assert lib.siss_abi_version() == _lib.ABI_VERSION
+    assert lib.siss_row_workspace_bytes(64) > 0 and lib.siss_norm3_workspace_bytes() > 0
+    assert "not sm_100" in _lib.error_string(-3)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must be rejected loudly, not silently computed some other way."""
+    from siss_b200 import ops
+    from siss_b200._lib import SissLibraryError
+    from siss_b200.losses import DDPMDeletionLoss
+    from siss_b200.scheduler import SissDDPMScheduler
+    x = torch.zeros(2, 1, 4, 4)
+    t = torch.zeros(2, dtype=torch.long)
+    sched = SissDDPMScheduler()
+    with pytest.raises(SissLibraryError):
+        sched.add_noise(x, x, t)
+    with pytest.raises(SissLibraryError):
+        ops.norm3(torch.zeros(8), torch.zeros(8))
+    gamma, sigma = sched.gamma_sigma("cpu")
+    loss = DDPMDeletionLoss(gamma, sigma)
+    d = {"og_latents": x, "noisy_latents": x}
+    with pytest.raises(SissLibraryError):
+        loss.importance_sampling_with_mixture(lambda *a, **k: (x,), t, x, {}, d, d, lambd=0.5)
+    with pytest.raises(SissLibraryError):
+        loss.naive_del(lambda *a, **k: (x,), t, x, {}, d, d)
+
+
+def test_product_does_not_import_oracle():
+    for p in (ROOT / "siss_b200").rglob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt and "siss_oracle" not in txt, p
+
+
+def test_scheduler_tables_match_oracle():
+    from oracle import siss_oracle as O
+    from siss_b200.scheduler import SissDDPMScheduler
+    s = SissDDPMScheduler()
+    assert torch.equal(s.alphas_cumprod, O.make_alphas_cumprod())
+    s = SissDDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    assert torch.equal(s.alphas_cumprod, O.make_alphas_cumprod(beta_start=0.00085, beta_end=0.012,
+                                                                beta_schedule="scaled_linear"))
+    g, sg = s.gamma_sigma("cpu")
+    og, os_ = O.gamma_sigma(s.alphas_cumprod)
+    assert torch.equal(g, og) and torch.equal(sg, os_)

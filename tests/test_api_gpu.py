@@ -1,0 +1,228 @@
+"""GPU: the reference-facing Python surface (DDPMDeletionLoss, GradCombiner, UnlearnStep) driven the
+way the task loops drive it (delete_celeb.py:580-767), compared with the golden fixtures and with the
+CPU oracle's literal restatement of that loop."""
+import copy
+
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, conditioning_of, load_golden, weight_tolerance
+from oracle import siss_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    from siss_b200 import _lib
+    _lib.load()
+    return cuda_device
+
+
+def _to(d, dev):
+    return {k: v.to(dev) for k, v in d.items()}
+
+
+def _close_w(got, exp, d_x, d_a):
+    got, exp = got.cpu().double(), exp.double()
+    tol = weight_tolerance(d_x.cpu(), d_a.cpu())
+    sat = exp == 0
+    assert torch.equal(got[sat], exp[sat])
+    assert (((got - exp).abs() / exp.clamp_min(1e-300))[~sat] <= tol[~sat]).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_drop_in_siss_matches_reference_outputs(name, dev):
+    """Same seeds, same call, same 7-tuple as the reference run that produced the fixture."""
+    from siss_b200.losses import DDPMDeletionLoss
+    c = load_golden(name)
+    loss = DDPMDeletionLoss(gamma=c["gamma"].to(dev), sigma=c["sigma"].to(dev))
+    unet = O.StubUNet().to(dev)
+    all_d = _to({"og_latents": c["x0"], "noisy_latents": c["xt_x"]}, dev)
+    del_d = _to({"og_latents": c["a0"], "noisy_latents": c["xt_a"]}, dev)
+    cond = _to(conditioning_of(c), dev)
+    torch.manual_seed(c["siss_mask_seed"])      # the Bernoulli mask comes from the CPU generator, as in the reference
+    loss_fn = getattr(loss, "importance_sampling_with_mixture")   # selected by name (delete_celeb.py:373-374)
+    items = loss_fn(unet, c["t"].to(dev), c["noise"].to(dev), cond, all_d, del_d, lambd=c["lambd"])
+    assert len(items) == 7 and items[0] is None
+    _, loss_x, loss_a, w_x, w_a, wl_x, wl_a = items
+    assert loss_x.dtype == torch.float32 and loss_x.shape == c["x0"].shape and wl_x.requires_grad
+    # weights: tolerance from the conditioning of the reference's own formula
+    from siss_b200 import ops
+    _, d_x, d_a, _, _ = ops.mixture_weights(all_d["noisy_latents"], del_d["noisy_latents"], all_d["og_latents"],
+                                            del_d["og_latents"], c["siss_keep_mask"], c["t"].to(dev), loss.all_gamma,
+                                            loss.all_sigma, c["lambd"])
+    _close_w(w_x, c["siss_w_x"], d_x, d_a); _close_w(w_a, c["siss_w_a"], d_x, d_a)
+    # element-wise losses do not depend on the weights: bit-exact
+    assert torch.equal(loss_x.cpu(), c["siss_loss_x"]) and torch.equal(loss_a.cpu(), c["siss_loss_a"])
+    tol = weight_tolerance(d_x.cpu(), d_a.cpu()).max().item()
+    torch.testing.assert_close(wl_x.detach().cpu(), c["siss_wl_x"], rtol=tol, atol=1e-30)
+    torch.testing.assert_close(wl_a.detach().cpu(), c["siss_wl_a"], rtol=tol, atol=1e-30)
+
+    # the task loop's two backward passes (delete_celeb.py:686-702)
+    B = c["x0"].shape[0]
+    (wl_x.sum() / B).backward(retain_graph=True)
+    gx = [p.grad.clone() for p in unet.parameters()]
+    (wl_a.sum() / B).backward()
+    ga = [p.grad - g for p, g in zip(unet.parameters(), gx)]
+    # oracle with the same mask
+    ounet = O.StubUNet()
+    oit = O.OracleDeletionLoss(c["gamma"], c["sigma"]).importance_sampling_with_mixture(
+        ounet, c["t"], c["noise"], conditioning_of(c), {"og_latents": c["x0"], "noisy_latents": c["xt_x"]},
+        {"og_latents": c["a0"], "noisy_latents": c["xt_a"]}, lambd=c["lambd"], keep_mask=c["siss_keep_mask"])
+    (oit[5].sum() / B).backward(retain_graph=True)
+    ogx = [p.grad.clone() for p in ounet.parameters()]
+    (oit[6].sum() / B).backward()
+    oga = [p.grad - g for p, g in zip(ounet.parameters(), ogx)]
+    for a, b in zip(gx + ga, ogx + oga):
+        torch.testing.assert_close(a.cpu(), b, rtol=max(tol, 1e-4), atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tshirt_fp32", "celeb_bf16_t999", "sd_fp32_cond", "fp16_mid_t", "odd_D_fp32"])
+def test_drop_in_other_methods(name, dev):
+    from siss_b200.losses import DDPMDeletionLoss
+    c = load_golden(name)
+    loss = DDPMDeletionLoss(gamma=c["gamma"].to(dev), sigma=c["sigma"].to(dev))
+    all_d = _to({"og_latents": c["x0"], "noisy_latents": c["xt_x"]}, dev)
+    del_d = _to({"og_latents": c["a0"], "noisy_latents": c["xt_a"]}, dev)
+    cond = _to(conditioning_of(c), dev)
+    t, noise = c["t"].to(dev), c["noise"].to(dev)
+
+    it = loss.double_forward_with_neg_del(O.StubUNet().to(dev), t, noise, cond, all_d, del_d)
+    assert it[0] is None and it[3] is None and it[4] is None and it[5] is it[1] and it[6] is it[2]
+    assert torch.equal(it[1].cpu(), c["nois_loss_x"]) and torch.equal(it[2].cpu(), c["nois_loss_a"])
+
+    it = loss.simple_neg_del(O.StubUNet().to(dev), t, noise, cond, all_d, del_d, superfactor=1.7)
+    assert it[1] is None and all(v is None for v in it[3:])
+    assert torch.equal(it[0].cpu(), c["neg_loss"]) and torch.equal(it[2].cpu(), c["neg_loss_a"])
+
+    unet = O.StubUNet().to(dev)
+    it = loss.naive_del(unet, t, noise, cond, all_d, del_d)
+    assert it[1] is it[0] and all(v is None for v in it[2:])
+    assert torch.equal(it[0].cpu(), c["naive_loss"])
+    (it[0].sum() / 4).backward()
+    ounet = O.StubUNet()
+    oit = O.OracleDeletionLoss(c["gamma"], c["sigma"]).naive_del(
+        ounet, c["t"], c["noise"], conditioning_of(c), {"og_latents": c["x0"], "noisy_latents": c["xt_x"]},
+        {"og_latents": c["a0"], "noisy_latents": c["xt_a"]})
+    (oit[0].sum() / 4).backward()
+    for p, q in zip(unet.parameters(), ounet.parameters()):
+        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=1e-4, atol=1e-5)
+
+    # EraseDiff draws its uniform target on the device generator (as the reference does when run on a
+    # GPU); loss_x is deterministic, loss_a is checked against that same device draw.
+    torch.manual_seed(99)
+    unet = O.StubUNet().to(dev)
+    it = loss.erasediff(unet, t, noise, cond, all_d, del_d)
+    assert torch.equal(it[1].cpu(), c["erasediff_loss_x"])
+    torch.manual_seed(99)
+    pred_a = unet(del_d["noisy_latents"], t, **cond)[0]
+    u = torch.rand_like(pred_a)
+    assert torch.equal(it[2], (pred_a - u) ** 2)
+
+
+class TinyNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(5)
+        self.c1 = torch.nn.Conv2d(1, 4, 3, padding=1)
+        self.c2 = torch.nn.Conv2d(4, 1, 3, padding=1)
+        self.odd = torch.nn.Parameter(torch.zeros(3))   # 3 elements: exercises the 16B padding between views
+
+    def forward(self, x, timesteps, return_dict=False, **kw):
+        return (self.c2(torch.tanh(self.c1(x))) + self.odd.sum(),)
+
+
+@pytest.mark.parametrize("loss_fn,kw", [
+    ("importance_sampling_with_mixture", dict(lambd=0.5, scaling_norm=5.0)),
+    ("double_forward_with_neg_del", dict(scaling_norm=500.0)),
+    ("naive_del", dict()),
+    ("simple_neg_del", dict(superfactor=0.3)),
+])
+@pytest.mark.parametrize("G", [1, 3])
+def test_unlearn_step_matches_reference_loop(loss_fn, kw, G, dev):
+    """Fast path (K1oK2, K3, dual buffers, K4) == the reference's loop (clone / subtract / dict
+    accumulate / per-tensor norms / clip) on the same batches and the same Bernoulli masks."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = 4
+    cpu_net = TinyNet()
+    gpu_net = copy.deepcopy(cpu_net).to(dev)
+    sched = SissDDPMScheduler()
+    gamma, sigma = O.gamma_sigma(sched.alphas_cumprod)
+    oloss = O.OracleDeletionLoss(gamma, sigma)
+    loop = O.ReferenceGradLoop(cpu_net, train_batch_size=B, grad_accum_steps=G)
+    comb = GradCombiner(gpu_net.parameters())
+    step = UnlearnStep(gpu_net, sched, comb, loss_fn=loss_fn, train_batch_size=B, gradient_accumulation_steps=G,
+                       max_norm=1.0, **kw)
+    torch.manual_seed(77)
+    for k in range(G):
+        x0, a0 = torch.rand(B, 1, 8, 8) * 2 - 1, torch.rand(B, 1, 8, 8) * 2 - 1
+        noise, t = torch.randn(B, 1, 8, 8), torch.randint(300, 1000, (B,))
+        keep = torch.rand(B) > 0.5
+        all_d = {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)}
+        del_d = {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}
+        okw = {}
+        if loss_fn == "importance_sampling_with_mixture":
+            okw = dict(lambd=0.5, keep_mask=keep)
+        elif loss_fn == "simple_neg_del":
+            okw = dict(superfactor=0.3)
+        items = getattr(oloss, loss_fn)(cpu_net, t, noise, {}, all_d, del_d, **okw)
+        loop.micro_step(items, retain_graph=(loss_fn == "importance_sampling_with_mixture"))
+        out = step.micro_step(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev), keep_mask=keep)
+        if items[1] is not None and "row_loss_x" in out:
+            torch.testing.assert_close(out["row_loss_x"].cpu(), items[1].detach().sum(dim=[1, 2, 3]), rtol=1e-4, atol=1e-5)
+    assert step.is_sync_step
+    single = loss_fn in ("naive_del", "simple_neg_del")
+    ref = loop.sync_step(single, loss_fn, scaling_norm=kw.get("scaling_norm"), max_norm=1.0)
+    stats = step.sync_step().cpu()
+    for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
+        assert p.grad.data_ptr() >= comb.g_x.data_ptr()          # grads live in the flat buffer
+        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-4, atol=2e-6)
+    if not single:
+        torch.testing.assert_close(stats[0], ref["norm_x"], rtol=1e-4, atol=0)
+        torch.testing.assert_close(stats[1], ref["norm_a"], rtol=1e-4, atol=0)
+        torch.testing.assert_close(stats[2], ref["scaling_factor"].float(), rtol=1e-4, atol=0)
+    torch.testing.assert_close(stats[3], ref["total_norm"], rtol=1e-4, atol=1e-7)
+    # second optimiser step reuses the buffers: G_a was cleared, G_x is cleared on begin_x
+    assert comb.g_a.abs().max().item() == 0.0
+
+
+def test_drop_in_loop_with_grad_combiner(dev):
+    """The reference loop written with the drop-in class + GradCombiner (the INTEGRATION.md recipe):
+    7-tuple -> .sum()/B -> backward twice with begin_x/begin_a -> combine."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.losses import DDPMDeletionLoss
+    from siss_b200.scheduler import SissDDPMScheduler
+    torch.backends.cudnn.allow_tf32 = False
+    B, G = 4, 2
+    cpu_net = TinyNet(); gpu_net = copy.deepcopy(cpu_net).to(dev)
+    sched = SissDDPMScheduler()
+    gamma, sigma = sched.gamma_sigma(dev)
+    loss_fn = DDPMDeletionLoss(gamma=gamma, sigma=sigma).importance_sampling_with_mixture
+    oloss = O.OracleDeletionLoss(*O.gamma_sigma(sched.alphas_cumprod))
+    loop = O.ReferenceGradLoop(cpu_net, train_batch_size=B, grad_accum_steps=G)
+    comb = GradCombiner(gpu_net.parameters())
+    torch.manual_seed(5)
+    for k in range(G):
+        x0, a0 = torch.rand(B, 1, 8, 8) * 2 - 1, torch.rand(B, 1, 8, 8) * 2 - 1
+        noise, t = torch.randn(B, 1, 8, 8), torch.randint(300, 1000, (B,))
+        keep = torch.rand(B) > 0.5
+        xt_x, xt_a = sched.add_noise_pair(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev))
+        items = loss_fn(gpu_net, t.to(dev), noise.to(dev), {}, {"og_latents": x0.to(dev), "noisy_latents": xt_x},
+                        {"og_latents": a0.to(dev), "noisy_latents": xt_a}, lambd=0.5, keep_mask=keep)
+        comb.begin_x(); (items[5].sum() / B / G).backward(retain_graph=True)
+        comb.begin_a(); (items[6].sum() / B / G).backward()
+        oit = oloss.importance_sampling_with_mixture(
+            cpu_net, t, noise, {}, {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)},
+            {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}, lambd=0.5, keep_mask=keep)
+        loop.micro_step(oit, retain_graph=True)
+    comb.combine(scaling_norm=5.0, max_norm=1.0)
+    loop.sync_step(False, scaling_norm=5.0, max_norm=1.0)
+    for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
+        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-4, atol=2e-6)
+    st = comb.stats_dict()
+    assert set(st) >= {"gradient/norm_loss_x", "gradient/norm_loss_a", "gradient/scaling_factor"}
