@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py — SISS loss + gradient-combine hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[1], ``delete_celeb``): CelebA-HQ-shaped synthetic batch, 3x256x256,
+bf16 images / noise, fp32 UNet output, t == 999 (delete_celeb.py:593-598), lambd = 0.5,
+scaling_norm = 500 (config/delete_celeb.yaml:18-22), per-GPU micro-batch 64 (= the reference's
+train_batch_size 4 x gradient_accumulation_steps 16 per optimiser step), gradient buffers of
+P = 113,673,219 parameters (google/ddpm-celebahq-256). The UNet itself is outside the path
+(BASELINE.json north_star) and is replaced by resident tensors (``value``) or a P-parameter stub (``e2e``).
+
+One "step" = one optimiser step's worth of the hot path:
+    K1oK2 siss_add_noise_mixture -> K3 siss_wmse_fwd_bwd -> [N>1: reduce-scatter G_x, G_a]
+    -> K4a siss_norm3 -> [N>1: all-reduce 3 scalars] -> K4b siss_combine -> [N>1: all-gather]
+
+  value  : samples/s, inputs resident in HBM, only the kernels above (+ NCCL collectives when N>1).
+  e2e    : samples/s through the public API (UnlearnStep + GradCombiner, P-parameter stub UNet, real
+           autograd), images copied host->device from pinned memory and the step's statistics copied
+           device->host every step.
+  --impl reference : the reference's CPU implementation of the same step (oracle port of the
+           reference loop, torch CPU, all host threads) — rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "SISS loss+grad-combine samples/s"
+UNIT = "samples/s"
+CELEB_PARAMS = 113_673_219  # google/ddpm-celebahq-256 UNet2DModel parameter count
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["siss", "reference"], default="siss")
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU micro-batch")
+    ap.add_argument("--params", type=int, default=CELEB_PARAMS)
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--channels", type=int, default=3)
+    ap.add_argument("--dtype", choices=["bf16", "fp32", "fp16"], default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    return ap.parse_args()
+
+
+def torch_dtype(name):
+    return {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[name]
+
+
+class BenchUNet(torch.nn.Module):
+    """UNet stand-in with P parameters whose forward/backward cost is a few streaming passes, so the
+    path under test is not masked: eps_hat = x * scale + bias + 1e-6 * sum(bank). Every parameter gets a
+    dense gradient through real autograd. Call convention of ddpm_deletion_loss.py:24."""
+
+    def __init__(self, n_params: int):
+        super().__init__()
+        self.scale = torch.nn.Parameter(torch.tensor(0.75))
+        self.bias = torch.nn.Parameter(torch.tensor(0.05))
+        self.bank = torch.nn.Parameter(torch.zeros(max(n_params - 2, 1)))
+
+    def forward(self, x, timesteps, return_dict=False, **kw):
+        return (x.float() * self.scale + (self.bias + self.bank.sum() * 1e-6),)
+
+
+def synth_images(shape, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    x0 = (torch.rand(shape, generator=g) * 2 - 1).to(dtype)  # data normalised to [-1, 1] (delete_celeb.yaml:28-34)
+    a0 = (torch.rand(shape, generator=g) * 2 - 1).to(dtype)
+    return x0, a0
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (NVML sampled in a thread during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle's restatement of the reference loop on host cores
+# --------------------------------------------------------------------------------------------------
+def make_cpu_step(args):
+    from oracle import siss_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    dt = torch_dtype(args.dtype)
+    B = args.batch
+    shape = (B, args.channels, args.res, args.res)
+    x0, a0 = synth_images(shape, dt, seed=42)
+    ac = O.make_alphas_cumprod()
+    gamma, sigma = O.gamma_sigma(ac)
+    loss = O.OracleDeletionLoss(gamma, sigma)
+    unet = BenchUNet(args.params)
+    loop = O.ReferenceGradLoop(unet, train_batch_size=B, grad_accum_steps=1)
+    torch.manual_seed(42)
+
+    def step():
+        # delete_celeb.py:581-603: shared noise, t == 999, two add_noise calls
+        noise = torch.randn(shape, dtype=dt)
+        t = torch.randint(999, 1000, (B,)).long()
+        all_d = {"og_latents": x0, "noisy_latents": O.add_noise(ac, x0, noise, t)}
+        del_d = {"og_latents": a0, "noisy_latents": O.add_noise(ac, a0, noise, t)}
+        items = loss.importance_sampling_with_mixture(unet, t, noise, {}, all_d, del_d, lambd=0.5)   # :622
+        stats = O.batch_stats(items)                                                                 # :626-656
+        loop.micro_step(items, retain_graph=True)                                                    # :686-711
+        out = loop.sync_step(False, scaling_norm=500.0, max_norm=1.0)                                # :714-767
+        stats["gradient/norm_loss_a"] = float(out["norm_a"])
+        for p in unet.parameters():                                                                  # zero_grad()
+            p.grad = None
+        return stats
+
+    return step, threads
+
+
+def time_cpu(args, steps, warmup):
+    step, threads = make_cpu_step(args)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return times, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU reference arm
+    times, threads = time_cpu(args, args.steps, args.warmup)
+    total = sum(times)
+    value = args.batch * len(times) / total
+    sample = (f"full workload per step: B={args.batch} x {args.channels}x{args.res}x{args.res} {args.dtype}, "
+              f"P={args.params} fp32 grads; {len(times)} timed steps after {args.warmup} warm-up")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {
+        "workload": "delete_celeb: SISS importance_sampling_with_mixture, lambd=0.5, scaling_norm=500, clip 1.0",
+        "per_gpu_batch": args.batch, "global_batch": args.batch * n, "shape": [args.channels, args.res, args.res],
+        "latent_dtype": args.dtype, "pred_dtype": "fp32", "timesteps": "t=999 (delete_celeb.py:593)",
+        "grad_params": args.params, "grad_accum": 1, "unet": "outside the path (resident eps_hat / P-param stub in e2e)",
+        "parallelism": f"dp{n}", "l2": "inputs larger than L2 (per-step footprint >> 126 MB); no flush",
+        "resident_step": "K1oK2 + K3 + K4a + K4b (+ reduce-scatter x2, scalar all-reduce, all-gather when N>1)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(kernel):
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_siss(args):
+    import torch.distributed as dist
+    from siss_b200 import ops, _lib
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep, batch_stats, upstream_scale
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl siss needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = world
+    _lib.load()
+
+    dt = torch_dtype(args.dtype)
+    B, D = args.batch, args.channels * args.res * args.res
+    shape = (B, args.channels, args.res, args.res)
+    P = args.params
+    lambd, scaling_norm, max_norm = 0.5, 500.0, 1.0
+    sched = SissDDPMScheduler()
+    ac = sched.alphas_cumprod.to(dev)
+    gamma, sigma = sched.gamma_sigma(dev)
+    go = upstream_scale(B * n, 1)  # loss is normalised by the GLOBAL batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- resident arm ("value")
+    x0_h, a0_h = synth_images(shape, dt, seed=42 + rank)
+    x0, a0 = x0_h.to(dev), a0_h.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    noise = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32).to(dt)
+    pred = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
+    t = torch.full((B,), 999, device=dev, dtype=torch.long)
+    keep = (torch.rand(B, generator=torch.Generator().manual_seed(7)) > lambd).to(torch.uint8).to(dev)
+    pad = 4 * n
+    Ptot = (P + pad - 1) // pad * pad
+    G_x = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
+    G_a = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
+    G_out = torch.empty_like(G_x)
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    stats5 = torch.zeros(5, device=dev)
+    if n > 1:
+        S = Ptot // n
+        sh_x, sh_a = torch.empty(S, device=dev), torch.empty(S, device=dev)
+
+    kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_norm3", "siss_combine"]
+    evs = {k: [] for k in kernels}
+
+    def timed(name, record, fn):
+        if not record:
+            return fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn()
+        e.record()
+        evs[name].append((s, e))
+        return r
+
+    def resident_step(record=False):
+        x_mix, _dx, _da, w_x, w_a = timed("siss_add_noise_mixture", record, lambda: ops.add_noise_mixture(
+            x0, a0, noise, keep, t, ac, gamma, sigma, lambd))
+        timed("siss_wmse_fwd_bwd", record, lambda: ops.wmse_fwd_bwd(pred, x_mix, x0, a0, t, gamma, sigma, w_x, w_a, go, go))
+        if n == 1:
+            timed("siss_norm3", record, lambda: ops.norm3(G_x, G_a, out=sums))
+            timed("siss_combine", record, lambda: ops.combine(G_x, G_a, sums, _lib.SISS_COMBINE_SCALING_NORM,
+                                                              scaling_norm, max_norm, out=G_out, stats=stats5))
+        else:
+            dist.reduce_scatter_tensor(sh_x, G_x)
+            dist.reduce_scatter_tensor(sh_a, G_a)
+            timed("siss_norm3", record, lambda: ops.norm3(sh_x, sh_a, out=sums))
+            dist.all_reduce(sums)
+            timed("siss_combine", record, lambda: ops.combine(sh_x, sh_a, sums, _lib.SISS_COMBINE_SCALING_NORM,
+                                                              scaling_norm, max_norm, out=sh_x, stats=stats5))
+            dist.all_gather_into_tensor(G_out, sh_x)
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    barrier()
+    launches0 = ops.launch_count
+    sampler = ClockSampler(local_rank)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        start.record()
+        for _ in range(args.steps):
+            resident_step(record=True)
+        end.record()
+        barrier()
+    gpu_launches = ops.launch_count - launches0
+    elapsed_ms = start.elapsed_time(end)
+    el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(el.item())
+    value = B * n * args.steps / (elapsed_ms / 1e3)
+    kernel_ms = {k: statistics.mean(s.elapsed_time(e) for s, e in v) for k, v in evs.items()}
+
+    # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md): s_in = bytes of the latent dtype
+    s_in = x0.element_size()
+    Pk = Ptot if n == 1 else Ptot // n
+    alg_bytes = {
+        "siss_add_noise_mixture": 4 * s_in * B * D,
+        "siss_wmse_fwd_bwd": (12 + 3 * s_in) * B * D,
+        "siss_norm3": 8 * Pk,
+        "siss_combine": 12 * Pk,
+    }
+    peak, peak_src = load_peaks()
+    per_kernel = {k: {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "gbs": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9,
+                      "frac": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak} for k in kernels}
+    dom = max(kernels, key=lambda k: kernel_ms[k])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per_kernel[dom]["frac"], "traffic": load_traffic(dom), "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes[dom], "ms_per_launch": kernel_ms[dom], "kernels": per_kernel,
+                "kernel_share_of_step": sum(kernel_ms.values()) / (elapsed_ms / args.steps)}
+
+    # ---------------------------------------------------------------- e2e arm (public API, host buffers)
+    e2e = None
+    if not args.no_e2e:
+        del G_out, pred
+        torch.cuda.empty_cache()
+        unet = BenchUNet(P).to(dev)
+        comb = GradCombiner(unet.parameters())
+        step = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B * n,
+                           lambd=lambd, scaling_norm=scaling_norm, max_norm=max_norm)
+        x0_p, a0_p = x0_h.pin_memory(), a0_h.pin_memory()
+        host_out = torch.empty(5 + 16, dtype=torch.float32).pin_memory()
+        done = torch.cuda.Event()
+        torch.manual_seed(42 + rank)
+
+        def e2e_step():
+            x0.copy_(x0_p, non_blocking=True)                 # dataset batch .to(device)   delete_celeb.py:560-564
+            a0.copy_(a0_p, non_blocking=True)
+            nz = torch.randn(shape, dtype=dt, device=dev)     # :581
+            ts = torch.randint(999, 1000, (B,), device=dev).long()   # :593
+            out = step.micro_step(x0, a0, nz, ts)             # CPU Bernoulli draw + 64 B H2D inside
+            bs = batch_stats(out, D)                          # :626-656 from the O(B) row sums
+            st = step.sync_step()
+            host_out.copy_(torch.cat([st, torch.stack(list(bs.values()))]), non_blocking=True)
+            done.record()
+            done.synchronize()                                # the loop reads its metrics every step
+            return host_out
+
+        for _ in range(max(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e2.record()
+        barrier()
+        el2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(el2.item())
+        assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics: {host_out}"
+        e2e = {"value": B * n * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * B * D * s_in + B), "d2h_bytes_per_step": int(host_out.numel() * 4),
+               "ms_per_step": e2e_ms / args.steps,
+               "api": "siss_b200.step.UnlearnStep.micro_step + sync_step (GradCombiner), BenchUNet(P) stub"}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1)
+    cpu_baseline = None
+    if rank == 0 and n == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        times, threads = time_cpu(args, args.cpu_steps, 1)
+        med = statistics.median(times)
+        cpu_baseline = {"value": B / med, "unit": UNIT, "cores": threads, "kind": "port",
+                        "ms_per_step": med * 1e3,
+                        "sample": (f"full workload per step (B={B}, P={P}), median of {len(times)} steps after 1 warm-up, "
+                                   "oracle port of the reference loop in torch CPU")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_siss(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -183,8 +183,8 @@ int siss_dual_mse_fwd_bwd(const void* pred_x, const void* pred_a, int pred_dtype
  * Replaces the per-parameter Python loops at delete_celeb.py:714-753 (= delete_tshirt.py:656-697,
  * delete_sd.py:1071-1109) and the clip at delete_celeb.py:767.
  *
- * K4a siss_norm3: sums3 = { sum g_x^2, sum g_a^2, sum g_x*g_a } as three doubles (fp32 products,
- * fp64 accumulation, fixed order). 8 bytes/parameter. `workspace` from siss_norm3_workspace_bytes,
+ * K4a siss_norm3: sums3 = { sum g_x^2, sum g_a^2, sum g_x*g_a } as three doubles (exact fp64
+ * products, fp64 accumulation, fixed order). 8 bytes/parameter. `workspace` from siss_norm3_workspace_bytes,
  * zeroed once.
  *
  * K4b siss_combine: reads sums3 FROM DEVICE MEMORY (so an all-reduce of the three scalars can sit

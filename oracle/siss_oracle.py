@@ -58,15 +58,27 @@ def gamma_sigma(alphas_cumprod: Tensor) -> Tuple[Tensor, Tensor]:
     return alphas_cumprod ** 0.5, (1 - alphas_cumprod) ** 0.5
 
 
+def _ieee_sqrt(v: Tensor) -> Tensor:
+    """``v ** 0.5`` with a correctly rounded square root. ATen evaluates ``pow(x, 0.5)`` as ``sqrt``
+    in fp32 (16-bit inputs are widened first) and rounds to ``v.dtype``. On CUDA that sqrt is IEEE;
+    torch-CPU's AVX-512 vectorised sqrt on the build host is NOT (about 0.6 % of inputs are 1 ulp off
+    the correctly rounded value — measured), so the oracle takes the root in float64
+    and rounds, which is exact for fp32. ``add_noise`` runs on the sample's device in the reference,
+    i.e. on the GPU, so IEEE is the behaviour to restate."""
+    if v.dtype == torch.float64:
+        return v.sqrt()
+    return v.double().sqrt().float().to(v.dtype)
+
+
 def add_noise(alphas_cumprod: Tensor, original_samples: Tensor, noise: Tensor, timesteps: Tensor) -> Tensor:
     """DDPMScheduler.add_noise: the table is cast to the SAMPLE dtype first, then gathered, then
     square-rooted; the two products and the sum are ordinary eager ops in the sample dtype."""
     ac = alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
     timesteps = timesteps.to(original_samples.device)
-    sqrt_alpha_prod = (ac[timesteps] ** 0.5).flatten()
+    sqrt_alpha_prod = _ieee_sqrt(ac[timesteps]).flatten()
     while sqrt_alpha_prod.dim() < original_samples.dim():
         sqrt_alpha_prod = sqrt_alpha_prod.unsqueeze(-1)
-    sqrt_one_minus = ((1 - ac[timesteps]) ** 0.5).flatten()
+    sqrt_one_minus = _ieee_sqrt(1 - ac[timesteps]).flatten()
     while sqrt_one_minus.dim() < original_samples.dim():
         sqrt_one_minus = sqrt_one_minus.unsqueeze(-1)
     return sqrt_alpha_prod * original_samples + sqrt_one_minus * noise

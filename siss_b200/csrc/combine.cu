@@ -1,5 +1,5 @@
 // K4: the two-term gradient combine on flat fp32 gradient buffers.
-//   K4a siss_norm3   : { sum g_x^2, sum g_a^2, sum g_x g_a }  (8 B/param)
+//   K4a siss_norm3   : { sum g_x^2, sum g_a^2, sum g_x g_a } in fp64 (8 B/param)
 //   K4b siss_combine : out = clip * (g_x - s * g_a)            (12 B/param)
 // Reference: delete_celeb.py:714-753 (+ delete_tshirt.py:688-690 inf guard) and the
 // clip_grad_norm_(1.0) at delete_celeb.py:767. See include/siss_b200.h.
@@ -54,8 +54,10 @@ norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long lo
                 ra[j] = ldg_stream(ga + 4 * i);
             }
         }
-        // fp32 products, fp32 sum over the <=16 elements of this iteration, fp64 across iterations
-        float sxx = 0.f, saa = 0.f, sxa = 0.f;
+        // Products and sums in fp64 (exact products of fp32 values): the clip needs
+        // ||g_x - s g_a||^2 = sxx - 2 s sxa + s^2 saa, which cancels when g_x ~ s g_a, so the three
+        // sums must be good to fp64 rounding, not fp32. 3 DFMA + 2 cvt per parameter is ~15% of the
+        // B200 fp64 pipe at HBM speed; the kernel stays memory-bound.
 #pragma unroll
         for (int j = 0; j < kK4Unroll; ++j) {
             if (!ok[j]) continue;
@@ -64,20 +66,20 @@ norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long lo
             VecTraits<float>::unpack(ra[j], a);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                sxx = fmaf(x[q], x[q], sxx);
-                saa = fmaf(a[q], a[q], saa);
-                sxa = fmaf(x[q], a[q], sxa);
+                const double xd = (double)x[q], ad = (double)a[q];
+                acc[0] = fma(xd, xd, acc[0]);
+                acc[1] = fma(ad, ad, acc[1]);
+                acc[2] = fma(xd, ad, acc[2]);
             }
         }
-        acc[0] += (double)sxx; acc[1] += (double)saa; acc[2] += (double)sxa;
     }
     // scalar remainder (n % 4 elements, or everything when the buffers are not 16B aligned)
     {
         const long long start = nvec * 4;
         const long long stride = (long long)gridDim.x * kThreads;
         for (long long i = start + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-            const float x = gx[i], a = ga[i];
-            acc[0] += (double)(x * x); acc[1] += (double)(a * a); acc[2] += (double)(x * a);
+            const double x = (double)gx[i], a = (double)ga[i];
+            acc[0] = fma(x, x, acc[0]); acc[1] = fma(a, a, acc[1]); acc[2] = fma(x, a, acc[2]);
         }
     }
 

@@ -1,71 +1,146 @@
-// Row tiling shared by the per-sample kernels (K1, K2, K3).
+// Work decomposition shared by the per-sample kernels (K1, K2, K3).
 //
 // Data layout: every image/latent tensor is contiguous [B, D]. A "unit" is one global access of
 // W elements of one stream: W = 16/sizeof(T) (one 128-bit access) on the vector path, W = 1 on
 // the scalar path taken when D is not a multiple of the vector width or a pointer is not 16-byte
-// aligned. A "tile" is `iters * VPT * kThreads` consecutive units of ONE row, processed by one
-// CTA; rows longer than a tile are split into `nch` tiles whose partial sums are combined in
-// fixed order by the last CTA to finish the row (common.cuh: last_cta_ticket). The host picks
-// `iters` so that the grid has a few tiles per resident CTA when the batch is small (so 148 SMs
-// stay busy at B = 4) and long tiles when it is large (fewer barriers per byte).
+// aligned. The flat unit space [0, U), U = B * ceil(D/W), is cut into `grid` CONTIGUOUS spans,
+// one per CTA (persistent grid = SMs x resident CTAs, or fewer when there is little work). A CTA
+// walks its span row segment by row segment: per-row scalars (t, gamma, sigma, mask, weights) are
+// fetched once per segment, per-row sums are accumulated in registers over the whole segment and
+// reduced ONCE per segment (warp shuffles -> smem). Long contiguous streams per CTA keep HBM pages
+// open; a CTA touches at most span/row_len + 2 rows.
+//
+// Rows that are split over several CTAs combine their partial sums through a small workspace:
+//   slot(cta c, row r) = c + r      (unique, because spans and rows are both monotone; < grid + B)
+//   contributors of row r = owner(first unit of r) .. owner(last unit of r)   (consecutive CTAs)
+// The last contributor to arrive (ticket counter per row) sums the slots in fixed order with one
+// warp (lane-strided, then butterfly), so results are bitwise reproducible for a given shape+GPU.
 #pragma once
 
 #include "common.cuh"
 
 namespace siss {
 
-constexpr int kMaxRowChunks = 128;  // max tiles per row (workspace: B * 128 * 4 floats)
-constexpr int kRowPartialStride = 4;  // floats per (row, chunk) partial slot
+constexpr int kMaxGrid = 148 * 8;         // upper bound on any row-kernel grid (slots workspace)
+constexpr int kRowPartialStride = 4;      // floats per partial slot (one 128-bit access)
 
-struct RowTiling {
+struct RowSched {
     long long B;
     long long D;
-    long long units_per_row;  // ceil(D / W); for the vector path D % W == 0
-    int iters;                // inner iterations per tile
-    int nch;                  // tiles per row
-    long long tiles;          // B * nch
-    int grid;                 // CTAs to launch (persistent, grid-stride over tiles)
+    long long upr;   // units per row = ceil(D / W)
+    long long U;     // total units = B * upr
+    int grid;        // CTAs to launch
 };
 
 int cached_sm_count();
 
-// ctas_per_sm: residency the kernel was compiled for (launch_bounds min blocks).
-inline RowTiling make_row_tiling(long long B, long long D, int W, int VPT, int ctas_per_sm) {
-    RowTiling rt;
-    rt.B = B; rt.D = D;
-    rt.units_per_row = (D + W - 1) / W;
-    const long long step = (long long)kThreads * VPT;        // units per inner iteration
-    const long long max_iters = (rt.units_per_row + step - 1) / step;
-    const long long slots = (long long)cached_sm_count() * ctas_per_sm;
-    // Largest power-of-two iters (<= 8) that still leaves >= 4 tiles per resident CTA slot.
-    long long iters = 8;
-    while (iters > 1) {
-        long long it = iters < max_iters ? iters : max_iters;
-        long long nch = (rt.units_per_row + step * it - 1) / (step * it);
-        if (B * nch >= 4 * slots) break;
-        iters >>= 1;
-    }
-    // ...but never more than kMaxRowChunks tiles per row (bounds the partial-sum workspace).
-    const long long min_iters = (rt.units_per_row + step * kMaxRowChunks - 1) / (step * kMaxRowChunks);
-    if (iters < min_iters) iters = min_iters;
-    if (iters > max_iters) iters = max_iters;
-    if (iters < 1) iters = 1;
-    rt.iters = (int)iters;
-    rt.nch = (int)((rt.units_per_row + step * iters - 1) / (step * iters));
-    rt.tiles = B * rt.nch;
-    rt.grid = (int)(rt.tiles < slots ? rt.tiles : slots);
-    if (rt.grid < 1) rt.grid = 1;
-    return rt;
+inline RowSched make_row_sched(long long B, long long D, int W, int ctas_per_sm) {
+    RowSched s;
+    s.B = B; s.D = D;
+    s.upr = (D + W - 1) / W;
+    s.U = B * s.upr;
+    long long slots = (long long)cached_sm_count() * ctas_per_sm;
+    if (slots > kMaxGrid) slots = kMaxGrid;
+    // at least one unit per thread per CTA; small problems use fewer, fully busy CTAs
+    long long want = (s.U + kThreads - 1) / kThreads;
+    s.grid = (int)(want < slots ? want : slots);
+    if (s.grid < 1) s.grid = 1;
+    return s;
 }
 
-template <typename T, int W>
-__device__ __forceinline__ void load_unit(const T* p, float (&f)[W]) {
-    if constexpr (W == 1) {
-        f[0] = VecTraits<T>::load1(p);
-    } else {
-        static_assert(W == VecTraits<T>::N, "vector width");
-        VecTraits<T>::unpack(ldg_stream(p), f);
+// span of CTA c: [floor(c U / G), floor((c+1) U / G))
+__device__ __forceinline__ void cta_span(const RowSched& s, long long& u0, long long& u1) {
+    const long long g = gridDim.x, c = blockIdx.x;
+    u0 = (c * s.U) / g;
+    u1 = ((c + 1) * s.U) / g;
+}
+
+// the CTA whose span contains unit u (inverse of the floor partition above)
+__device__ __forceinline__ int span_owner(const RowSched& s, long long u) {
+    return (int)(((u + 1) * (long long)gridDim.x - 1) / s.U);
+}
+
+// torch-style index: negative wraps once, then clamp for memory safety (eager would raise).
+__device__ __forceinline__ int wrap_timestep(long long t, int T) {
+    if (t < 0) t += T;
+    if (t < 0) t = 0;
+    if (t >= T) t = T - 1;
+    return (int)t;
+}
+
+// Workspace: [B] ticket counters (zero between launches; the kernels restore that) followed by
+// (kMaxGrid + B) partial slots of kRowPartialStride floats.
+struct RowWorkspace {
+    unsigned int* counters;
+    float* partials;
+};
+
+inline long long row_ws_counter_bytes(long long B) {
+    return ((B * (long long)sizeof(unsigned int) + 255) / 256) * 256;
+}
+
+inline long long row_ws_bytes(long long B) {
+    return row_ws_counter_bytes(B) + (B + kMaxGrid) * (long long)kRowPartialStride * (long long)sizeof(float);
+}
+
+inline RowWorkspace carve_row_workspace(void* ws, long long B) {
+    RowWorkspace r;
+    r.counters = reinterpret_cast<unsigned int*>(ws);
+    r.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + row_ws_counter_bytes(B));
+    return r;
+}
+
+// 128-bit L2-coherent load/store of a partial slot (other SMs wrote it: bypass L1)
+__device__ __forceinline__ float4 ld_slot(const float* p) {
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_slot(float* p, float a, float b, float c) {
+    asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+}
+
+// Reduce K (<= 3) per-thread sums over the CTA and, if the row is shared with other CTAs, over
+// all contributors. Returns true in exactly the threads of warp 0 of the CTA that ends up holding
+// the complete row totals (`tot`): the only contributor, or the last one to arrive.
+// Call from ALL threads (contains __syncthreads).
+template <int K>
+__device__ __forceinline__ bool row_reduce(float (&acc)[K], double (&tot)[K], const RowSched& s, const RowWorkspace& ws,
+                                           long long row, float* red, int* flag) {
+    static_assert(K <= 3, "slot holds 3 values");
+    block_sum<K>(acc, red);
+    const long long rs = row * s.upr;
+    const int first = span_owner(s, rs), last = span_owner(s, rs + s.upr - 1);
+    if (first == last) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) tot[k] = (double)acc[k];
+        return threadIdx.x < 32;
     }
+    // Only thread 0 publishes, so only thread 0 needs the (expensive, store-draining) device fence.
+    if (threadIdx.x == 0) {
+        st_slot(ws.partials + ((long long)blockIdx.x + row) * kRowPartialStride, acc[0], K > 1 ? acc[1] : 0.f,
+                K > 2 ? acc[2] : 0.f);
+        __threadfence();
+        unsigned int* counter = ws.counters + row;
+        const unsigned int tk = atomicAdd(counter, 1u);
+        const int is_last = (tk == (unsigned)(last - first));
+        if (is_last) *counter = 0u;  // leave the workspace clean for the next launch
+        *flag = is_last;
+    }
+    __syncthreads();
+    if (*flag == 0 || threadIdx.x >= 32) return false;
+    __threadfence();  // acquire side
+    double t[3] = {0.0, 0.0, 0.0};
+    const float* base = ws.partials + ((long long)first + row) * kRowPartialStride;
+    const int n = last - first + 1;
+    for (int i = threadIdx.x; i < n; i += 32) {
+        const float4 v = ld_slot(base + (long long)i * kRowPartialStride);
+        t[0] += (double)v.x; t[1] += (double)v.y; t[2] += (double)v.z;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) tot[k] = warp_sum(t[k]);
+    return true;
 }
 
 template <typename T, int W>
@@ -73,11 +148,12 @@ __device__ __forceinline__ void store_unit(T* p, const float (&f)[W]) {
     if constexpr (W == 1) {
         VecTraits<T>::store1(p, f[0]);
     } else {
+        static_assert(W == VecTraits<T>::N, "vector width");
         stg_stream(p, VecTraits<T>::pack(f));
     }
 }
 
-// Raw 128-bit fetch used to batch all loads of an iteration before the first use (MLP).
+// Raw fetch used to batch all loads of an iteration before the first use (MLP).
 template <typename T, int W> struct RawUnit { uint4 v; };
 template <typename T> struct RawUnit<T, 1> { float v; };
 
@@ -93,30 +169,14 @@ __device__ __forceinline__ void decode_raw(const RawUnit<T, W>& r, float (&f)[W]
     else VecTraits<T>::unpack(r.v, f);
 }
 
-// torch-style index: negative wraps once, then clamp for memory safety (eager would raise).
-__device__ __forceinline__ int wrap_timestep(long long t, int T) {
-    if (t < 0) t += T;
-    if (t < 0) t = 0;
-    if (t >= T) t = T - 1;
-    return (int)t;
-}
-
-// Workspace for cross-CTA row reductions: [B] ticket counters (zero between launches; the
-// kernels restore that) followed by [B][kMaxRowChunks][kRowPartialStride] fp32 partial slots.
-struct RowWorkspace {
-    unsigned int* counters;
-    float* partials;
-};
-
-inline long long row_ws_counter_bytes(long long B) {
-    return ((B * (long long)sizeof(unsigned int) + 255) / 256) * 256;
-}
-
-inline RowWorkspace carve_row_workspace(void* ws, long long B) {
-    RowWorkspace r;
-    r.counters = reinterpret_cast<unsigned int*>(ws);
-    r.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + row_ws_counter_bytes(B));
-    return r;
+// Row segment of the CTA span [u0, u1) that lies in `row`; unit indices relative to the row start.
+struct RowSeg { long long begin, end; };
+__device__ __forceinline__ RowSeg row_segment(const RowSched& s, long long u0, long long u1, long long row) {
+    const long long rb = row * s.upr;
+    RowSeg g;
+    g.begin = (u0 > rb ? u0 - rb : 0);
+    g.end = (u1 < rb + s.upr ? u1 - rb : s.upr);
+    return g;
 }
 
 }  // namespace siss

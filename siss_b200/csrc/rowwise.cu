@@ -49,22 +49,23 @@ template <typename T, int W, int NSRC>
 __global__ void __launch_bounds__(kThreads, kK1Occ)
 add_noise_kernel(const T* __restrict__ x0, const T* __restrict__ a0, const T* __restrict__ noise,
                  const int64_t* __restrict__ ts, const float* __restrict__ ac, int T_steps,
-                 T* __restrict__ xt_x, T* __restrict__ xt_a, RowTiling rt) {
+                 T* __restrict__ xt_x, T* __restrict__ xt_a, RowSched s) {
     constexpr int VPT = kK1Vpt;
-    const long long step = (long long)kThreads * VPT;
-    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
-        const long long row = tile / rt.nch;
-        const int ch = (int)(tile - row * rt.nch);
+    long long u0, u1;
+    cta_span(s, u0, u1);
+    if (u0 >= u1) return;
+    for (long long row = u0 / s.upr; row * s.upr < u1; ++row) {
+        const RowSeg sg = row_segment(s, u0, u1, row);
         float sa, s1;
         noise_coeffs<T>(ac, wrap_timestep(ts[row], T_steps), sa, s1);
-        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
-        for (int it = 0; it < rt.iters; ++it) {
+        const long long rowoff = row * s.D;
+        for (long long ub = sg.begin; ub < sg.end; ub += (long long)kThreads * VPT) {
             RawUnit<T, W> rx[VPT], ra[VPT], rn[VPT];
             long long e[VPT];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const long long u = ubase + it * step + (long long)j * kThreads;
-                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                const long long u = ub + (long long)j * kThreads + threadIdx.x;
+                e[j] = (u < sg.end) ? (rowoff + u * W) : -1;
                 if (e[j] >= 0) {
                     fetch_raw<T, W>(x0 + e[j], rx[j]);
                     if (NSRC == 2) fetch_raw<T, W>(a0 + e[j], ra[j]);
@@ -99,13 +100,13 @@ static int launch_add_noise(const void* x0, const void* a0, const void* noise, c
     bool vec = (D % N == 0) && aligned16(x0) && aligned16(noise) && aligned16(xt_x);
     if (NSRC == 2) vec = vec && aligned16(a0) && aligned16(xt_a);
     if (vec) {
-        RowTiling rt = make_row_tiling(B, D, N, kK1Vpt, kK1Occ);
-        add_noise_kernel<T, N, NSRC><<<rt.grid, kThreads, 0, st>>>(
-            (const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a, rt);
+        RowSched s = make_row_sched(B, D, N, kK1Occ);
+        add_noise_kernel<T, N, NSRC><<<s.grid, kThreads, 0, st>>>(
+            (const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a, s);
     } else {
-        RowTiling rt = make_row_tiling(B, D, 1, kK1Vpt, kK1Occ);
-        add_noise_kernel<T, 1, NSRC><<<rt.grid, kThreads, 0, st>>>(
-            (const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a, rt);
+        RowSched s = make_row_sched(B, D, 1, kK1Occ);
+        add_noise_kernel<T, 1, NSRC><<<s.grid, kThreads, 0, st>>>(
+            (const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a, s);
     }
     return (int)cudaGetLastError();
 }
@@ -114,7 +115,7 @@ static int launch_add_noise(const void* x0, const void* a0, const void* noise, c
 // K2 and K1 o K2
 // ---------------------------------------------------------------------------------------------
 constexpr int kK2Vpt = 2;
-constexpr int kK2Occ = 4;
+constexpr int kK2Occ = 3;
 
 // Row epilogue (one thread): losses/ddpm_deletion_loss.py:34,38 (division by 2 sigma^2) and
 // :41-45 (ratios and weights), in the reference's fp32 op order. `sd` is the directly
@@ -147,48 +148,49 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
                float lam, float one_m_lam,
                T* __restrict__ x_mix, float* __restrict__ dist_x, float* __restrict__ dist_a,
                float* __restrict__ w_x, float* __restrict__ w_a,
-               RowWorkspace ws, RowTiling rt) {
+               RowWorkspace ws, RowSched s) {
     constexpr int VPT = kK2Vpt;
     __shared__ float red[3 * kWarps];
     __shared__ int flag;
-    const long long step = (long long)kThreads * VPT;
+    long long u0, u1;
+    cta_span(s, u0, u1);
+    if (u0 >= u1) return;
 
-    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
-        const long long row = tile / rt.nch;
-        const int ch = (int)(tile - row * rt.nch);
+    for (long long row = u0 / s.upr; row * s.upr < u1; ++row) {
+        const RowSeg sg = row_segment(s, u0, u1, row);
         const int t = wrap_timestep(ts[row], T_steps);
         const bool k = keep[row] != 0;
         const float g = gamma[t];
         float sa = 0.f, s1 = 0.f;
         if (FUSED_NOISE) noise_coeffs<T>(ac, t, sa, s1);
-        const T* __restrict__ sel = FUSED_NOISE ? (k ? x0 : a0) : (k ? src_x : src_a);
+        // third stream: eps when fused, otherwise the selected noisy row
+        const T* __restrict__ third = FUSED_NOISE ? noise : (k ? src_x : src_a);
+        const long long rowoff = row * s.D;
 
         float acc[3] = {0.f, 0.f, 0.f};  // sum r_x^2, sum r_a^2, sum (r_x^2 - r_a^2)
-        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
-        for (int it = 0; it < rt.iters; ++it) {
+        for (long long ub = sg.begin; ub < sg.end; ub += (long long)kThreads * VPT) {
             RawUnit<T, W> rx[VPT], ra[VPT], rs[VPT];
             long long e[VPT];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const long long u = ubase + it * step + (long long)j * kThreads;
-                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                const long long u = ub + (long long)j * kThreads + threadIdx.x;
+                e[j] = (u < sg.end) ? (rowoff + u * W) : -1;
                 if (e[j] >= 0) {
                     fetch_raw<T, W>(x0 + e[j], rx[j]);
                     fetch_raw<T, W>(a0 + e[j], ra[j]);
-                    // FUSED: the third stream is eps; otherwise the selected noisy row.
-                    fetch_raw<T, W>((FUSED_NOISE ? noise : sel) + e[j], rs[j]);
+                    fetch_raw<T, W>(third + e[j], rs[j]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
                 if (e[j] < 0) continue;
-                float x[W], a[W], s[W], m[W];
+                float x[W], a[W], v[W], m[W];
                 decode_raw<T, W>(rx[j], x);
                 decode_raw<T, W>(ra[j], a);
-                decode_raw<T, W>(rs[j], s);
+                decode_raw<T, W>(rs[j], v);
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
-                    m[q] = FUSED_NOISE ? noised<T>(sa, s1, k ? x[q] : a[q], s[q]) : s[q];
+                    m[q] = FUSED_NOISE ? noised<T>(sa, s1, k ? x[q] : a[q], v[q]) : v[q];
                     const float r_x = __fsub_rn(m[q], __fmul_rn(g, x[q]));
                     const float r_a = __fsub_rn(m[q], __fmul_rn(g, a[q]));
                     acc[0] = fmaf(r_x, r_x, acc[0]);
@@ -199,28 +201,9 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
             }
         }
 
-        block_sum<3>(acc, red);
-        if (rt.nch == 1) {
-            if (threadIdx.x == 0)
-                finalize_row_weights(acc[0], acc[1], acc[2], sigma[t], lam, one_m_lam, row,
-                                     dist_x, dist_a, w_x, w_a);
-        } else {
-            float* slot = ws.partials + (row * kMaxRowChunks + ch) * kRowPartialStride;
-            if (threadIdx.x == 0) { slot[0] = acc[0]; slot[1] = acc[1]; slot[2] = acc[2]; }
-            if (last_cta_ticket(ws.counters + row, (unsigned)rt.nch, &flag)) {
-                if (threadIdx.x == 0) {
-                    double sx = 0.0, sy = 0.0, sd = 0.0;
-                    const volatile float* p = ws.partials + row * kMaxRowChunks * kRowPartialStride;
-                    for (int c = 0; c < rt.nch; ++c) {
-                        sx += (double)p[c * kRowPartialStride + 0];
-                        sy += (double)p[c * kRowPartialStride + 1];
-                        sd += (double)p[c * kRowPartialStride + 2];
-                    }
-                    finalize_row_weights(sx, sy, sd, sigma[t], lam, one_m_lam, row,
-                                         dist_x, dist_a, w_x, w_a);
-                }
-            }
-        }
+        double tot[3];
+        if (row_reduce<3>(acc, tot, s, ws, row, red, &flag) && threadIdx.x == 0)
+            finalize_row_weights(tot[0], tot[1], tot[2], sigma[t], lam, one_m_lam, row, dist_x, dist_a, w_x, w_a);
     }
 }
 
@@ -238,15 +221,15 @@ static int launch_mixture(const void* src_x, const void* src_a, const void* x0, 
     vec = vec && (FUSED ? aligned16(noise) : (aligned16(src_x) && aligned16(src_a)));
     RowWorkspace ws = carve_row_workspace(workspace, B);
     if (vec) {
-        RowTiling rt = make_row_tiling(B, D, N, kK2Vpt, kK2Occ);
-        mixture_kernel<T, N, FUSED><<<rt.grid, kThreads, 0, st>>>(
+        RowSched s = make_row_sched(B, D, N, kK2Occ);
+        mixture_kernel<T, N, FUSED><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, rt);
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, s);
     } else {
-        RowTiling rt = make_row_tiling(B, D, 1, kK2Vpt, kK2Occ);
-        mixture_kernel<T, 1, FUSED><<<rt.grid, kThreads, 0, st>>>(
+        RowSched s = make_row_sched(B, D, 1, kK2Occ);
+        mixture_kernel<T, 1, FUSED><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, rt);
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, s);
     }
     return (int)cudaGetLastError();
 }
@@ -267,7 +250,7 @@ extern "C" {
 
 int64_t siss_row_workspace_bytes(int64_t B) {
     if (B < 1) B = 1;
-    return row_ws_counter_bytes(B) + B * (int64_t)kMaxRowChunks * kRowPartialStride * (int64_t)sizeof(float);
+    return row_ws_bytes(B);
 }
 
 int siss_add_noise(const void* x0, const void* noise, const int64_t* timesteps,

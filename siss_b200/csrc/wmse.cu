@@ -16,31 +16,6 @@ __device__ __forceinline__ float residual(float pred, float xm, float g, float s
     return __fsub_rn(pred, __fdiv_rn(__fsub_rn(xm, __fmul_rn(g, x)), sg));
 }
 
-// Per-row combine of two partial sums + publish (shared by K3 and the dual-MSE kernel).
-__device__ __forceinline__ void publish_row_sums2(float (&acc)[2], float* red, int* flag, const RowWorkspace& ws,
-                                                  const RowTiling& rt, long long row, int ch,
-                                                  float* __restrict__ out0, float* __restrict__ out1) {
-    block_sum<2>(acc, red);
-    if (rt.nch == 1) {
-        if (threadIdx.x == 0) { out0[row] = acc[0]; out1[row] = acc[1]; }
-        return;
-    }
-    float* slot = ws.partials + (row * kMaxRowChunks + ch) * kRowPartialStride;
-    if (threadIdx.x == 0) { slot[0] = acc[0]; slot[1] = acc[1]; }
-    if (last_cta_ticket(ws.counters + row, (unsigned)rt.nch, flag)) {
-        if (threadIdx.x == 0) {
-            double s0 = 0.0, s1 = 0.0;
-            const volatile float* p = ws.partials + row * kMaxRowChunks * kRowPartialStride;
-            for (int c = 0; c < rt.nch; ++c) {
-                s0 += (double)p[c * kRowPartialStride + 0];
-                s1 += (double)p[c * kRowPartialStride + 1];
-            }
-            out0[row] = (float)s0;
-            out1[row] = (float)s1;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // K3 fast path. TP = dtype of pred and of both gradients, T = dtype of x_mix / x0 / a0.
 // One unit = W elements where W = elements per 128-bit access of the NARROWER-count stream:
@@ -96,16 +71,18 @@ wmse_fwd_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, co
                     const float* __restrict__ w_x, const float* __restrict__ w_a, float go_x, float go_a,
                     TP* __restrict__ grad_x, TP* __restrict__ grad_a,
                     float* __restrict__ row_loss_x, float* __restrict__ row_loss_a,
-                    RowWorkspace ws, RowTiling rt) {
+                    RowWorkspace ws, RowSched rt) {
     constexpr int VPT = kK3Vpt;
     using PIO = PredIO<TP, W, VEC>;
     __shared__ float red[2 * kWarps];
     __shared__ int flag;
-    const long long step = (long long)kThreads * VPT;
 
-    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
-        const long long row = tile / rt.nch;
-        const int ch = (int)(tile - row * rt.nch);
+    long long u0, u1;
+    cta_span(rt, u0, u1);
+    if (u0 >= u1) return;
+    for (long long row = u0 / rt.upr; row * rt.upr < u1; ++row) {
+        const RowSeg seg = row_segment(rt, u0, u1, row);
+        const long long rowoff = row * rt.D;
         const int t = wrap_timestep(ts[row], T_steps);
         const float g = gamma[t], sg = sigma[t];
         // autograd: grad(weighted_loss) = go ; grad(loss) = go * w  (mul backward, rounded once)
@@ -113,15 +90,14 @@ wmse_fwd_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, co
         const float ca = __fmul_rn(go_a, w_a[row]);
 
         float acc[2] = {0.f, 0.f};
-        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
-        for (int it = 0; it < rt.iters; ++it) {
+        for (long long ub = seg.begin; ub < seg.end; ub += (long long)kThreads * VPT) {
             typename PIO::Raw rp[VPT];
             RawUnit<T, W> rm[VPT], rx[VPT], ra[VPT];
             long long e[VPT];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const long long u = ubase + it * step + (long long)j * kThreads;
-                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                const long long u = ub + (long long)j * kThreads + threadIdx.x;
+                e[j] = (u < seg.end) ? (rowoff + u * W) : -1;
                 if (e[j] >= 0) {
                     PIO::fetch(pred + e[j], rp[j]);
                     fetch_raw<T, W>(x_mix + e[j], rm[j]);
@@ -151,7 +127,11 @@ wmse_fwd_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, co
                 PIO::store(grad_a + e[j], ga);
             }
         }
-        publish_row_sums2(acc, red, &flag, ws, rt, row, ch, row_loss_x, row_loss_a);
+        double tot[2];
+        if (row_reduce<2>(acc, tot, rt, ws, row, red, &flag) && threadIdx.x == 0) {
+            row_loss_x[row] = (float)tot[0];
+            row_loss_a[row] = (float)tot[1];
+        }
     }
 }
 
@@ -165,26 +145,27 @@ wmse_fwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, const 
                 const float* __restrict__ gamma, const float* __restrict__ sigma, int T_steps,
                 const float* __restrict__ w_x, const float* __restrict__ w_a,
                 float* __restrict__ loss_x, float* __restrict__ loss_a,
-                float* __restrict__ wloss_x, float* __restrict__ wloss_a, RowTiling rt) {
+                float* __restrict__ wloss_x, float* __restrict__ wloss_a, RowSched rt) {
     constexpr int VPT = kK3Vpt;
     using PIO = PredIO<TP, W, VEC>;
     using OIO = PredIO<float, W, VEC>;
-    const long long step = (long long)kThreads * VPT;
-    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
-        const long long row = tile / rt.nch;
-        const int ch = (int)(tile - row * rt.nch);
+    long long u0, u1;
+    cta_span(rt, u0, u1);
+    if (u0 >= u1) return;
+    for (long long row = u0 / rt.upr; row * rt.upr < u1; ++row) {
+        const RowSeg seg = row_segment(rt, u0, u1, row);
+        const long long rowoff = row * rt.D;
         const int t = wrap_timestep(ts[row], T_steps);
         const float g = gamma[t], sg = sigma[t];
         const float wx = w_x[row], wa = w_a[row];
-        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
-        for (int it = 0; it < rt.iters; ++it) {
+        for (long long ub = seg.begin; ub < seg.end; ub += (long long)kThreads * VPT) {
             typename PIO::Raw rp[VPT];
             RawUnit<T, W> rm[VPT], rx[VPT], ra[VPT];
             long long e[VPT];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const long long u = ubase + it * step + (long long)j * kThreads;
-                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                const long long u = ub + (long long)j * kThreads + threadIdx.x;
+                e[j] = (u < seg.end) ? (rowoff + u * W) : -1;
                 if (e[j] >= 0) {
                     PIO::fetch(pred + e[j], rp[j]);
                     fetch_raw<T, W>(x_mix + e[j], rm[j]);
@@ -239,11 +220,10 @@ wmse_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, const 
                 const float* __restrict__ gamma, const float* __restrict__ sigma, int T_steps,
                 const float* __restrict__ w_x, const float* __restrict__ w_a,
                 GradOut go_lx, GradOut go_la, GradOut go_wx, GradOut go_wa,
-                TP* __restrict__ grad_pred, RowTiling rt) {
+                TP* __restrict__ grad_pred, RowSched rt) {
     constexpr int VPT = 1;
     using PIO = PredIO<TP, W, VEC>;
     using GIO = PredIO<float, W, VEC>;
-    const long long step = (long long)kThreads * VPT;
     // broadcast upstream scalars (what `.sum()` backward provides)
     const float s_lx = (go_lx.p && go_lx.stride == 0) ? go_lx.p[0] : 0.f;
     const float s_la = (go_la.p && go_la.stride == 0) ? go_la.p[0] : 0.f;
@@ -253,17 +233,19 @@ wmse_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, const 
     const bool d_wx = go_wx.p && go_wx.stride != 0, d_wa = go_wa.p && go_wa.stride != 0;
     const bool use_x = go_lx.p || go_wx.p, use_a = go_la.p || go_wa.p;
 
-    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
-        const long long row = tile / rt.nch;
-        const int ch = (int)(tile - row * rt.nch);
+    long long u0, u1;
+    cta_span(rt, u0, u1);
+    if (u0 >= u1) return;
+    for (long long row = u0 / rt.upr; row * rt.upr < u1; ++row) {
+        const RowSeg seg = row_segment(rt, u0, u1, row);
+        const long long rowoff = row * rt.D;
         const int t = wrap_timestep(ts[row], T_steps);
         const float g = gamma[t], sg = sigma[t];
         const float wx = w_x[row], wa = w_a[row];
-        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
-        for (int it = 0; it < rt.iters; ++it) {
-            const long long u = ubase + it * step;
-            if (u >= rt.units_per_row) continue;
-            const long long e = row * rt.D + u * W;
+        for (long long ub = seg.begin; ub < seg.end; ub += (long long)kThreads * VPT) {
+            const long long u = ub + threadIdx.x;
+            if (u >= seg.end) continue;
+            const long long e = rowoff + u * W;
             typename PIO::Raw rp;
             RawUnit<T, W> rm, rx, ra;
             typename GIO::Raw r1, r2, r3, r4;
@@ -331,7 +313,7 @@ sqerr_fwd_kernel(const TP* __restrict__ pred, const TT* __restrict__ tgt, TO* __
         const float u = VO::round(__fsub_rn(VecTraits<TP>::load1(pred + i), VecTraits<TT>::load1(tgt + i)));
         const float l = VO::round(__fmul_rn(u, u));
         VO::store1(loss + i, l);
-        if (scaled) VO::store1(scaled + i, VO::round(__fmul_rn(VO::round(alpha), l)));
+        if (scaled) VO::store1(scaled + i, VO::round(__fmul_rn(alpha, l)));  // scalar stays fp32 (opmath)
     }
 }
 
@@ -370,7 +352,7 @@ sqerr_bwd_kernel(const TP* __restrict__ pred, const TT* __restrict__ tgt,
         bool first = true;
         if (go_scaled) {
             const float gs = VO::load1(go_scaled + (go_scaled_stride ? i : 0));
-            const float c = VO::round(__fmul_rn(gs, VO::round(alpha)));  // mul backward: grad * alpha
+            const float c = VO::round(__fmul_rn(gs, alpha));  // mul backward: grad * alpha (fp32 opmath scalar)
             acc = VO::round(__fmul_rn(c, two_u)); first = false;
         }
         if (go_loss) {
@@ -391,28 +373,29 @@ dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
                 const TT* __restrict__ tgt_x, const TT* __restrict__ tgt_a, float go_x, float go_a,
                 TP* __restrict__ grad_x, TP* __restrict__ grad_a,
                 float* __restrict__ row_loss_x, float* __restrict__ row_loss_a,
-                RowWorkspace ws, RowTiling rt) {
+                RowWorkspace ws, RowSched rt) {
     constexpr int VPT = kK3Vpt;
     using PIO = PredIO<TP, W, VEC>;
     using TIO = PredIO<TT, W, VEC>;
     __shared__ float red[2 * kWarps];
     __shared__ int flag;
-    const long long step = (long long)kThreads * VPT;
     const bool shared_tgt = (tgt_a == tgt_x);
 
-    for (long long tile = blockIdx.x; tile < rt.tiles; tile += gridDim.x) {
-        const long long row = tile / rt.nch;
-        const int ch = (int)(tile - row * rt.nch);
+    long long u0, u1;
+    cta_span(rt, u0, u1);
+    if (u0 >= u1) return;
+    for (long long row = u0 / rt.upr; row * rt.upr < u1; ++row) {
+        const RowSeg seg = row_segment(rt, u0, u1, row);
+        const long long rowoff = row * rt.D;
         float acc[2] = {0.f, 0.f};
-        const long long ubase = (long long)ch * step * rt.iters + threadIdx.x;
-        for (int it = 0; it < rt.iters; ++it) {
+        for (long long ub = seg.begin; ub < seg.end; ub += (long long)kThreads * VPT) {
             typename PIO::Raw rpx[VPT], rpa[VPT];
             typename TIO::Raw rtx[VPT], rta[VPT];
             long long e[VPT];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const long long u = ubase + it * step + (long long)j * kThreads;
-                e[j] = (u < rt.units_per_row) ? (row * rt.D + u * W) : -1;
+                const long long u = ub + (long long)j * kThreads + threadIdx.x;
+                e[j] = (u < seg.end) ? (rowoff + u * W) : -1;
                 if (e[j] >= 0) {
                     PIO::fetch(pred_x + e[j], rpx[j]);
                     PIO::fetch(pred_a + e[j], rpa[j]);
@@ -441,7 +424,11 @@ dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
                 PIO::store(grad_a + e[j], ga);
             }
         }
-        publish_row_sums2(acc, red, &flag, ws, rt, row, ch, row_loss_x, row_loss_a);
+        double tot[2];
+        if (row_reduce<2>(acc, tot, rt, ws, row, red, &flag) && threadIdx.x == 0) {
+            row_loss_x[row] = (float)tot[0];
+            row_loss_a[row] = (float)tot[1];
+        }
     }
 }
 
@@ -468,12 +455,12 @@ static int launch_wmse_fwd_bwd(const void* pred, const void* x_mix, const void* 
     constexpr int W = VecTraits<T>::N;
     RowWorkspace ws = carve_row_workspace(workspace, B);
     if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a)) {
-        RowTiling rt = make_row_tiling(B, D, W, kK3Vpt, kK3Occ);
+        RowSched rt = make_row_sched(B, D, W, kK3Occ);
         wmse_fwd_bwd_kernel<TP, T, W, true><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             go_x, go_a, (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a, ws, rt);
     } else {
-        RowTiling rt = make_row_tiling(B, D, 1, kK3Vpt, kK3Occ);
+        RowSched rt = make_row_sched(B, D, 1, kK3Occ);
         wmse_fwd_bwd_kernel<TP, T, 1, false><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             go_x, go_a, (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a, ws, rt);
@@ -488,12 +475,12 @@ static int launch_wmse_fwd(const void* pred, const void* x_mix, const void* x0, 
                            float* wloss_x, float* wloss_a, long long B, long long D, cudaStream_t st) {
     constexpr int W = VecTraits<T>::N;
     if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, loss_x, loss_a, wloss_x, wloss_a)) {
-        RowTiling rt = make_row_tiling(B, D, W, kK3Vpt, kK3Occ);
+        RowSched rt = make_row_sched(B, D, W, kK3Occ);
         wmse_fwd_kernel<TP, T, W, true><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             loss_x, loss_a, wloss_x, wloss_a, rt);
     } else {
-        RowTiling rt = make_row_tiling(B, D, 1, kK3Vpt, kK3Occ);
+        RowSched rt = make_row_sched(B, D, 1, kK3Occ);
         wmse_fwd_kernel<TP, T, 1, false><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             loss_x, loss_a, wloss_x, wloss_a, rt);
@@ -512,12 +499,12 @@ static int launch_wmse_bwd(const void* pred, const void* x_mix, const void* x0, 
     for (const GradOut& g : gs)
         if (g.p && g.stride != 0) vec = vec && aligned16(g.p);
     if (vec) {
-        RowTiling rt = make_row_tiling(B, D, W, 1, kK3Occ);
+        RowSched rt = make_row_sched(B, D, W, kK3Occ);
         wmse_bwd_kernel<TP, T, W, true><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             g1, g2, g3, g4, (TP*)grad_pred, rt);
     } else {
-        RowTiling rt = make_row_tiling(B, D, 1, 1, kK3Occ);
+        RowSched rt = make_row_sched(B, D, 1, kK3Occ);
         wmse_bwd_kernel<TP, T, 1, false><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             g1, g2, g3, g4, (TP*)grad_pred, rt);
@@ -536,12 +523,12 @@ static int launch_dual_mse(const void* pred_x, const void* pred_a, const void* t
     const bool vec = (D % W == 0) && aligned16(pred_x) && aligned16(pred_a) && aligned16(tgt_x) &&
                      aligned16(tgt_a) && aligned16(grad_x) && aligned16(grad_a);
     if (vec) {
-        RowTiling rt = make_row_tiling(B, D, W, kK3Vpt, kK3Occ);
+        RowSched rt = make_row_sched(B, D, W, kK3Occ);
         dual_mse_kernel<TP, TT, W, true><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred_x, (const TP*)pred_a, (const TT*)tgt_x, (const TT*)tgt_a, go_x, go_a,
             (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a, ws, rt);
     } else {
-        RowTiling rt = make_row_tiling(B, D, 1, kK3Vpt, kK3Occ);
+        RowSched rt = make_row_sched(B, D, 1, kK3Occ);
         dual_mse_kernel<TP, TT, 1, false><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred_x, (const TP*)pred_a, (const TT*)tgt_x, (const TT*)tgt_a, go_x, go_a,
             (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a, ws, rt);

@@ -123,6 +123,8 @@ def add_noise(x0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
     ts = _timesteps(timesteps, B)
     ac = _table(alphas_cumprod, dev)
     out = torch.empty_like(x0)
+    if out.numel() == 0:
+        return out
     _lib.check(_lib.load().siss_add_noise(_ptr(x0), _ptr(noise), _ptr(ts), _ptr(ac), ac.numel(), _ptr(out),
                                           B, D, _dt(x0), _stream()), "siss_add_noise")
     _count()
@@ -140,6 +142,8 @@ def add_noise_pair(x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, time
     ts = _timesteps(timesteps, B)
     ac = _table(alphas_cumprod, dev)
     xt_x, xt_a = torch.empty_like(x0), torch.empty_like(a0)
+    if xt_x.numel() == 0:
+        return xt_x, xt_a
     _lib.check(_lib.load().siss_add_noise_pair(_ptr(x0), _ptr(a0), _ptr(noise), _ptr(ts), _ptr(ac), ac.numel(),
                                                _ptr(xt_x), _ptr(xt_a), B, D, _dt(x0), _stream()),
                "siss_add_noise_pair")

@@ -62,7 +62,7 @@ def test_add_noise_bit_exact(name, dev):
 def test_add_noise_vs_oracle_shapes(dtype, shape, dev):
     """ragged / odd D (scalar path), rows longer than one tile, more rows than CTAs, every timestep edge."""
     from siss_b200.scheduler import SissDDPMScheduler
-    torch.manual_seed(hash((str(dtype), shape)) % 2**31)
+    torch.manual_seed(sum(shape) * 131 + {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dtype])
     sched = SissDDPMScheduler()
     x0 = (torch.rand(shape) * 2 - 1).to(dtype)
     a0 = (torch.rand(shape) * 2 - 1).to(dtype)
@@ -283,23 +283,30 @@ def test_dual_mse(shape, td, dev):
 @pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096 * 5 + 1, (1 << 21) + 7])
 @pytest.mark.parametrize("mode", ["scaling_norm", "erasediff"])
 def test_norm3_combine_vs_oracle(n, mode, dev):
+    """K4a/K4b vs the oracle evaluated in float64 (tight) and in float32 (loose: the CPU reference's
+    own fp32 norm / dot reductions are only good to ~1e-5..1e-4 at 2M elements, measured)."""
     from siss_b200 import ops, _lib
     torch.manual_seed(n % 1000 + 1)
     gx, ga = torch.randn(n) * 3e-2, torch.randn(n) * 1e-2 + 2e-3
     kw = dict(scaling_norm=5.0) if mode == "scaling_norm" else dict(eta=0.05)
-    exp, nx, na, s, tn, clip = O.combine_flat(gx, ga, max_norm=1.0, **kw)
     sums = ops.norm3(gx.to(dev), ga.to(dev))
     ref = torch.tensor([(gx.double() ** 2).sum(), (ga.double() ** 2).sum(), (gx.double() * ga.double()).sum()])
-    torch.testing.assert_close(sums.cpu(), ref, rtol=1e-6, atol=1e-12)
+    torch.testing.assert_close(sums.cpu(), ref, rtol=1e-12, atol=1e-300)     # exact fp64 products
     m = _lib.SISS_COMBINE_SCALING_NORM if mode == "scaling_norm" else _lib.SISS_COMBINE_ERASEDIFF
     out, stats = ops.combine(gx.to(dev), ga.to(dev), sums, m, 5.0 if mode == "scaling_norm" else 0.05, 1.0)
-    st = stats.cpu()
-    torch.testing.assert_close(st[0], nx, rtol=1e-5, atol=0); torch.testing.assert_close(st[1], na, rtol=1e-5, atol=0)
-    # erasediff's s = eta - <x,a>/||a||^2 carries the CPU reference's own fp32 dot-product noise
-    torch.testing.assert_close(st[2], s.float(), rtol=1e-5, atol=1e-5 if mode == "erasediff" else 1e-8)
-    torch.testing.assert_close(st[3], tn, rtol=2e-5, atol=1e-8)
-    torch.testing.assert_close(st[4], clip.float(), rtol=2e-5, atol=0)
-    torch.testing.assert_close(out.cpu(), exp, rtol=2e-5, atol=1e-7)
+    st = stats.cpu().double()
+    for dtype, rtol in ((torch.float64, 2e-6), (torch.float32, 2e-4)):
+        exp, nx, na, s, tn, clip = O.combine_flat(gx.to(dtype), ga.to(dtype), max_norm=1.0, **kw)
+        scale = float(exp.abs().max())
+        torch.testing.assert_close(st[0], nx.double(), rtol=rtol, atol=0)
+        torch.testing.assert_close(st[1], na.double(), rtol=rtol, atol=0)
+        torch.testing.assert_close(st[2], s.double(), rtol=rtol, atol=rtol * 0.1)
+        torch.testing.assert_close(st[3], tn.double(), rtol=rtol, atol=1e-8)
+        torch.testing.assert_close(st[4], clip.double(), rtol=rtol, atol=0)
+        # x - s a cancels element-wise where x ~ s a (and s itself is an fp32 value): absolute tolerance
+        # relative to the tensor's scale and to the magnitude of the two terms being subtracted
+        mag = float((gx.double().abs() + (s.double() * ga.double()).abs()).max())
+        torch.testing.assert_close(out.cpu().double(), exp.double(), rtol=rtol, atol=max(rtol * scale, 4e-7 * mag))
 
 
 def test_combine_inplace_misaligned_and_guards(dev):
@@ -312,7 +319,7 @@ def test_combine_inplace_misaligned_and_guards(dev):
     sums = ops.norm3(gx, ga)
     out, _ = ops.combine(gx, ga, sums, _lib.SISS_COMBINE_SCALING_NORM, 500.0, 1.0, out=gx)  # aliasing g_x
     assert out.data_ptr() == gx.data_ptr()
-    torch.testing.assert_close(gx.cpu(), exp, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(gx.cpu(), exp, rtol=1e-4, atol=1e-4 * float(exp.abs().max()))
     # zero NegGrad gradient: s = inf without the guard (celeb/sd), 0 with it (tshirt)
     z = torch.zeros(64, device=dev); x = torch.ones(64, device=dev) * 0.01
     sums = ops.norm3(x, z)
