@@ -299,6 +299,49 @@ def combine_flat(g_x: Tensor, g_a: Tensor, scaling_norm: Optional[float] = None,
     return grad, norm_x, norm_a, torch.as_tensor(s, dtype=grad.dtype), total_norm, clip
 
 
+def norm3_cpu(g_x: Tensor, g_a: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """CPU stand-in for K4a (``siss_norm3``): the three sums in float64. Used ONLY by the gloo tests
+    that exercise GradCombiner's collective choreography on a CPU box."""
+    r = torch.stack([(g_x.double() ** 2).sum(), (g_a.double() ** 2).sum(), (g_x.double() * g_a.double()).sum()])
+    if out is None:
+        return r
+    out.copy_(r)
+    return out
+
+
+def combine_from_sums_cpu(g_x: Tensor, g_a: Tensor, sums3: Tensor, mode: int, value: float, max_norm: float = 1.0,
+                          inf_guard: bool = False, out: Optional[Tensor] = None, stats: Optional[Tensor] = None):
+    """CPU stand-in for K4b (``siss_combine``): same scalar logic (scaling factor per mode, norm of the
+    combination obtained algebraically from the three sums, clip coefficient), fp32 element-wise
+    update. mode: 0 scaling_norm, 1 erasediff, 2 none. Test infrastructure only."""
+    f32 = torch.float32
+    sxx, saa, sxa = (float(v) for v in sums3.tolist())
+    n_x = torch.sqrt(torch.tensor(sxx, dtype=f32))
+    n_a = torch.sqrt(torch.tensor(saa, dtype=f32))
+    if mode == 2:
+        s = torch.zeros((), dtype=f32)
+    elif mode == 1:
+        s = torch.tensor(value, dtype=f32) - torch.tensor(sxa, dtype=f32) / (n_a * n_a)
+        s = -(s if not (0.0 > s) else torch.zeros((), dtype=f32))
+    else:
+        s = torch.tensor(value, dtype=f32) / n_a
+        if inf_guard and torch.isinf(s):
+            s = torch.zeros((), dtype=f32)
+    sd = float(s)
+    tn = torch.tensor(max(sxx - 2.0 * sd * sxa + sd * sd * saa, 0.0), dtype=torch.float64).sqrt().to(f32)
+    clip = torch.ones((), dtype=f32)
+    if max_norm and max_norm > 0:
+        clip = torch.clamp(torch.tensor(max_norm, dtype=f32) / (tn + 1e-6), max=1.0)
+    res = (g_x - s * g_a) * clip
+    if out is None:
+        out = res
+    else:
+        out.copy_(res)
+    if stats is not None:
+        stats.copy_(torch.stack([n_x, n_a, s, tn, clip]))
+    return out, stats
+
+
 # --------------------------------------------------------------------------------------------------
 # Per-batch statistics (delete_celeb.py:626-656) — consumed by the stats tests
 # --------------------------------------------------------------------------------------------------

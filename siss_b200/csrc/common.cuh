@@ -64,6 +64,14 @@ template <> struct VecTraits<float> {
                           __float_as_uint(f[2]), __float_as_uint(f[3]));
     }
     __device__ static __forceinline__ float round(float v) { return v; }
+    // one unit of x_t = sa*x + s1*n in eager's order (mul, mul, add; no FMA contraction)
+    __device__ static __forceinline__ uint4 noised_unit(float sa, float s1, const uint4& x, const uint4& n) {
+        float xf[4], nf[4], o[4];
+        unpack(x, xf); unpack(n, nf);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __fadd_rn(__fmul_rn(sa, xf[i]), __fmul_rn(s1, nf[i]));
+        return pack(o);
+    }
     __device__ static __forceinline__ float load1(const float* p) { return *p; }
     __device__ static __forceinline__ void store1(float* p, float v) { *p = v; }
 };
@@ -90,6 +98,23 @@ template <> struct VecTraits<__nv_bfloat16> {
     __device__ static __forceinline__ float round(float v) {
         return __bfloat162float(__float2bfloat16_rn(v));
     }
+    // Packed native bf16 arithmetic (HMUL2/HADD2.BF16, two elements per instruction, no cvt): each
+    // op rounds once to bf16, which equals eager's "compute in fp32, round to bf16" because the fp32
+    // product of two bf16 values is exact and the fp32 sum cannot land on a bf16 tie unless the exact
+    // sum does. The _rn intrinsics forbid contraction into HFMA2. sa/s1 are bf16-representable.
+    __device__ static __forceinline__ uint4 noised_unit(float sa, float s1, const uint4& x, const uint4& n) {
+        const __nv_bfloat162 sa2 = __float2bfloat162_rn(sa), s12 = __float2bfloat162_rn(s1);
+        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, nw[4] = {n.x, n.y, n.z, n.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&xw[i]);
+            const __nv_bfloat162 nv = *reinterpret_cast<const __nv_bfloat162*>(&nw[i]);
+            const __nv_bfloat162 r = __hadd2_rn(__hmul2_rn(sa2, xv), __hmul2_rn(s12, nv));
+            o[i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
     __device__ static __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
@@ -114,6 +139,20 @@ template <> struct VecTraits<__half> {
         return make_uint4(w[0], w[1], w[2], w[3]);
     }
     __device__ static __forceinline__ float round(float v) { return __half2float(__float2half_rn(v)); }
+    // Packed native fp16 arithmetic; same argument as for bf16 (11-bit significands: exact fp32 product).
+    __device__ static __forceinline__ uint4 noised_unit(float sa, float s1, const uint4& x, const uint4& n) {
+        const __half2 sa2 = __float2half2_rn(sa), s12 = __float2half2_rn(s1);
+        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, nw[4] = {n.x, n.y, n.z, n.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half2 xv = *reinterpret_cast<const __half2*>(&xw[i]);
+            const __half2 nv = *reinterpret_cast<const __half2*>(&nw[i]);
+            const __half2 r = __hadd2_rn(__hmul2_rn(sa2, xv), __hmul2_rn(s12, nv));
+            o[i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
     __device__ static __forceinline__ float load1(const __half* p) { return __half2float(*p); }
     __device__ static __forceinline__ void store1(__half* p, float v) { *p = __float2half_rn(v); }
 };

@@ -6,7 +6,9 @@
 // fp32 math in registers, 128-bit stores. K2 additionally reduces three sums per row with
 // warp shuffles -> smem -> fixed-order cross-CTA combine.
 
-#include "rowtile.cuh"
+#include "bulkpipe.cuh"
+
+#include <cstdlib>
 
 namespace siss {
 
@@ -19,6 +21,16 @@ int cached_sm_count() {
             sms = kNumSMsB200;
     }
     return sms;
+}
+
+// A/B switch for measurements: SISS_NO_TMA=1 forces the plain-LDG kernels on the vector path too.
+bool use_tma_pipeline() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SISS_NO_TMA");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // sqrt(abar_t) and sqrt(1 - abar_t) the way diffusers 0.27.2 DDPMScheduler.add_noise forms them:
@@ -92,6 +104,39 @@ add_noise_kernel(const T* __restrict__ x0, const T* __restrict__ a0, const T* __
     }
 }
 
+// TMA-pipelined K1 (vector path): see bulkpipe.cuh.
+template <typename T, int NSRC>
+struct AddNoiseOp {
+    static constexpr int W = VecTraits<T>::N;
+    static constexpr int NIN = NSRC + 1;
+    static constexpr int K = 0;
+    static constexpr int kOcc = 3;
+    static constexpr int kStages = 6;
+    __host__ __device__ static constexpr int ub(int) { return 16; }
+    struct Params {
+        const T* x0; const T* a0; const T* noise; const int64_t* ts; const float* ac; int T_steps;
+        T* xt_x; T* xt_a;
+    };
+    struct Row { float sa, s1; };
+    __device__ static __forceinline__ Row row_begin(const Params& p, long long row) {
+        Row r;
+        noise_coeffs<T>(p.ac, wrap_timestep(p.ts[row], p.T_steps), r.sa, r.s1);
+        return r;
+    }
+    __device__ static __forceinline__ const char* stream(const Params& p, long long, int i) {
+        if (i == 0) return reinterpret_cast<const char*>(p.noise);
+        if (i == 1) return reinterpret_cast<const char*>(p.x0);
+        return reinterpret_cast<const char*>(p.a0);
+    }
+    __device__ static __forceinline__ void unit(const Params& p, const Row& r, const uint4 (&in)[NIN][2],
+                                                long long unit_index, float (&)[1]) {
+        stg_stream(p.xt_x + unit_index * W, VecTraits<T>::noised_unit(r.sa, r.s1, in[1][0], in[0][0]));
+        if constexpr (NSRC == 2)
+            stg_stream(p.xt_a + unit_index * W, VecTraits<T>::noised_unit(r.sa, r.s1, in[2][0], in[0][0]));
+    }
+    __device__ static __forceinline__ void row_end(const Params&, const Row&, long long, const double (&)[1]) {}
+};
+
 template <typename T, int NSRC>
 static int launch_add_noise(const void* x0, const void* a0, const void* noise, const int64_t* ts,
                             const float* ac, int T_steps, void* xt_x, void* xt_a,
@@ -99,6 +144,11 @@ static int launch_add_noise(const void* x0, const void* a0, const void* noise, c
     constexpr int N = VecTraits<T>::N;
     bool vec = (D % N == 0) && aligned16(x0) && aligned16(noise) && aligned16(xt_x);
     if (NSRC == 2) vec = vec && aligned16(a0) && aligned16(xt_a);
+    if (vec && use_tma_pipeline()) {
+        using Op = AddNoiseOp<T, NSRC>;
+        typename Op::Params p{(const T*)x0, (const T*)a0, (const T*)noise, ts, ac, T_steps, (T*)xt_x, (T*)xt_a};
+        return launch_pipe<Op>(p, RowWorkspace{nullptr, nullptr}, B, D, N, st);
+    }
     if (vec) {
         RowSched s = make_row_sched(B, D, N, kK1Occ);
         add_noise_kernel<T, N, NSRC><<<s.grid, kThreads, 0, st>>>(
@@ -207,6 +257,61 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
     }
 }
 
+// TMA-pipelined K2 / K1oK2 (vector path): see bulkpipe.cuh.
+template <typename T, bool FUSED_NOISE>
+struct MixtureOp {
+    static constexpr int W = VecTraits<T>::N;
+    static constexpr int NIN = 3;
+    static constexpr int K = 3;
+    static constexpr int kOcc = 3;
+    static constexpr int kStages = 6;   // 6 x 12 KB = 72 KB per CTA, 3 CTAs/SM
+    __host__ __device__ static constexpr int ub(int) { return 16; }
+    struct Params {
+        const T* src_x; const T* src_a; const T* x0; const T* a0; const T* noise;
+        const uint8_t* keep; const int64_t* ts; const float* ac; const float* gamma; const float* sigma;
+        int T_steps; float lam, one_m_lam;
+        T* x_mix; float* dist_x; float* dist_a; float* w_x; float* w_a;
+    };
+    struct Row { int t; bool k; float g, sa, s1; };
+    __device__ static __forceinline__ Row row_begin(const Params& p, long long row) {
+        Row r;
+        r.t = wrap_timestep(p.ts[row], p.T_steps);
+        r.k = p.keep[row] != 0;
+        r.g = p.gamma[r.t];
+        r.sa = 0.f; r.s1 = 0.f;
+        if (FUSED_NOISE) noise_coeffs<T>(p.ac, r.t, r.sa, r.s1);
+        return r;
+    }
+    __device__ static __forceinline__ const char* stream(const Params& p, long long row, int i) {
+        if (i == 0) return reinterpret_cast<const char*>(p.x0);
+        if (i == 1) return reinterpret_cast<const char*>(p.a0);
+        return reinterpret_cast<const char*>(FUSED_NOISE ? p.noise : (p.keep[row] != 0 ? p.src_x : p.src_a));
+    }
+    __device__ static __forceinline__ void unit(const Params& p, const Row& r, const uint4 (&in)[NIN][2],
+                                                long long unit_index, float (&acc)[3]) {
+        float x[W], a[W], m[W];
+        VecTraits<T>::unpack(in[0][0], x);
+        VecTraits<T>::unpack(in[1][0], a);
+        // x_t of the selected source (packed 16-bit arithmetic, no conversions), or the given noisy row
+        const uint4 mraw = FUSED_NOISE ? VecTraits<T>::noised_unit(r.sa, r.s1, r.k ? in[0][0] : in[1][0], in[2][0])
+                                       : in[2][0];
+        VecTraits<T>::unpack(mraw, m);
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const float r_x = __fsub_rn(m[q], __fmul_rn(r.g, x[q]));
+            const float r_a = __fsub_rn(m[q], __fmul_rn(r.g, a[q]));
+            acc[0] = fmaf(r_x, r_x, acc[0]);
+            acc[1] = fmaf(r_a, r_a, acc[1]);
+            acc[2] = fmaf(r_x - r_a, r_x + r_a, acc[2]);
+        }
+        stg_stream(p.x_mix + unit_index * W, mraw);
+    }
+    __device__ static __forceinline__ void row_end(const Params& p, const Row& r, long long row, const double (&tot)[3]) {
+        finalize_row_weights(tot[0], tot[1], tot[2], p.sigma[r.t], p.lam, p.one_m_lam, row, p.dist_x, p.dist_a,
+                             p.w_x, p.w_a);
+    }
+};
+
 template <typename T, bool FUSED>
 static int launch_mixture(const void* src_x, const void* src_a, const void* x0, const void* a0,
                           const void* noise, const uint8_t* keep, const int64_t* ts, const float* ac,
@@ -220,6 +325,12 @@ static int launch_mixture(const void* src_x, const void* src_a, const void* x0, 
     bool vec = (D % N == 0) && aligned16(x0) && aligned16(a0) && aligned16(x_mix);
     vec = vec && (FUSED ? aligned16(noise) : (aligned16(src_x) && aligned16(src_a)));
     RowWorkspace ws = carve_row_workspace(workspace, B);
+    if (vec && use_tma_pipeline()) {
+        using Op = MixtureOp<T, FUSED>;
+        typename Op::Params p{(const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
+                              gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a};
+        return launch_pipe<Op>(p, ws, B, D, N, st);
+    }
     if (vec) {
         RowSched s = make_row_sched(B, D, N, kK2Occ);
         mixture_kernel<T, N, FUSED><<<s.grid, kThreads, 0, st>>>(

@@ -6,9 +6,11 @@
 // outputs are bit-identical to the reference's ATen sequence; only the per-row sums differ in
 // reduction order.
 
-#include "rowtile.cuh"
+#include "bulkpipe.cuh"
 
 namespace siss {
+
+bool use_tma_pipeline();
 
 // u_x = pred - (x_mix - gamma*x0)/sigma  — losses/ddpm_deletion_loss.py:26,29 in eager's order:
 // mul, sub, div, sub, each rounded to fp32.
@@ -433,6 +435,144 @@ dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA-pipelined fast paths (vector path): see bulkpipe.cuh. A unit is W = 16/sizeof(T) elements of
+// the latent dtype; the pred / gradient side of a unit is W * sizeof(TP) bytes = 16 or 32.
+// ---------------------------------------------------------------------------------------------
+template <typename TP, int W>
+__device__ __forceinline__ void decode_pred(const uint4 (&in)[2], float (&f)[W]) {
+    constexpr int NP = VecTraits<TP>::N;
+    if constexpr (NP >= W) {
+        float tmp[NP];
+        VecTraits<TP>::unpack(in[0], tmp);
+#pragma unroll
+        for (int q = 0; q < W; ++q) f[q] = tmp[q];
+    } else {
+        static_assert(2 * NP == W, "pred unit is at most two 128-bit accesses");
+        float a[NP], b[NP];
+        VecTraits<TP>::unpack(in[0], a);
+        VecTraits<TP>::unpack(in[1], b);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { f[q] = a[q]; f[NP + q] = b[q]; }
+    }
+}
+
+template <typename TP, int W>
+__device__ __forceinline__ void store_pred(TP* p, const float (&f)[W]) {
+    constexpr int NP = VecTraits<TP>::N;
+    static_assert(NP == W || 2 * NP == W, "pred unit is one or two 128-bit accesses");
+#pragma unroll
+    for (int i = 0; i < W / NP; ++i) {
+        float tmp[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) tmp[q] = f[i * NP + q];
+        stg_stream(p + i * NP, VecTraits<TP>::pack(tmp));
+    }
+}
+
+template <typename TP, typename T>
+struct WmseFwdBwdOp {
+    static constexpr int W = VecTraits<T>::N;
+    static constexpr int PB = W * (int)sizeof(TP);   // pred bytes per unit: 16 or 32
+    static constexpr int NIN = 4;
+    static constexpr int K = 2;
+    static constexpr int kOcc = 2;
+    static constexpr int kStages = (PB == 32) ? 5 : 6;   // 5 x 20 KB or 6 x 16 KB per CTA, 2 CTAs/SM
+    __host__ __device__ static constexpr int ub(int i) { return i == 0 ? PB : 16; }
+    struct Params {
+        const TP* pred; const T* x_mix; const T* x0; const T* a0; const int64_t* ts;
+        const float* gamma; const float* sigma; int T_steps; const float* w_x; const float* w_a;
+        float go_x, go_a; TP* grad_x; TP* grad_a; float* row_loss_x; float* row_loss_a;
+    };
+    struct Row { float g, sg, cx, ca; };
+    __device__ static __forceinline__ Row row_begin(const Params& p, long long row) {
+        Row r;
+        const int t = wrap_timestep(p.ts[row], p.T_steps);
+        r.g = p.gamma[t]; r.sg = p.sigma[t];
+        r.cx = __fmul_rn(p.go_x, p.w_x[row]);   // mul backward: grad * w, rounded once
+        r.ca = __fmul_rn(p.go_a, p.w_a[row]);
+        return r;
+    }
+    __device__ static __forceinline__ const char* stream(const Params& p, long long, int i) {
+        if (i == 0) return reinterpret_cast<const char*>(p.pred);
+        if (i == 1) return reinterpret_cast<const char*>(p.x_mix);
+        if (i == 2) return reinterpret_cast<const char*>(p.x0);
+        return reinterpret_cast<const char*>(p.a0);
+    }
+    __device__ static __forceinline__ void unit(const Params& p, const Row& r, const uint4 (&in)[NIN][2],
+                                                long long unit_index, float (&acc)[2]) {
+        float pr[W], m[W], x[W], a[W], gx[W], ga[W];
+        decode_pred<TP, W>(in[0], pr);
+        VecTraits<T>::unpack(in[1][0], m);
+        VecTraits<T>::unpack(in[2][0], x);
+        VecTraits<T>::unpack(in[3][0], a);
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const float ux = residual(pr[q], m[q], r.g, r.sg, x[q]);
+            const float ua = residual(pr[q], m[q], r.g, r.sg, a[q]);
+            acc[0] = fmaf(ux, ux, acc[0]);
+            acc[1] = fmaf(ua, ua, acc[1]);
+            gx[q] = __fmul_rn(r.cx, __fmul_rn(2.0f, ux));   // pow backward: grad * (2 u)
+            ga[q] = __fmul_rn(r.ca, __fmul_rn(2.0f, ua));
+        }
+        store_pred<TP, W>(p.grad_x + unit_index * W, gx);
+        store_pred<TP, W>(p.grad_a + unit_index * W, ga);
+    }
+    __device__ static __forceinline__ void row_end(const Params& p, const Row&, long long row, const double (&tot)[2]) {
+        p.row_loss_x[row] = (float)tot[0];
+        p.row_loss_a[row] = (float)tot[1];
+    }
+};
+
+// Dual MSE: unit = WU elements, WU = max(elements per 128 bits of pred, of target).
+template <typename TP, typename TT, bool SHARED_TGT>
+struct DualMseOp {
+    static constexpr int NP = VecTraits<TP>::N, NT = VecTraits<TT>::N;
+    static constexpr int W = NP > NT ? NP : NT;
+    static constexpr int PB = W * (int)sizeof(TP);
+    static constexpr int TB = W * (int)sizeof(TT);
+    static constexpr int NIN = SHARED_TGT ? 3 : 4;
+    static constexpr int K = 2;
+    static constexpr int kOcc = 2;
+    static constexpr int kStages = 4;
+    __host__ __device__ static constexpr int ub(int i) { return i < 2 ? PB : TB; }
+    struct Params {
+        const TP* pred_x; const TP* pred_a; const TT* tgt_x; const TT* tgt_a; float go_x, go_a;
+        TP* grad_x; TP* grad_a; float* row_loss_x; float* row_loss_a;
+    };
+    struct Row { int unused; };
+    __device__ static __forceinline__ Row row_begin(const Params&, long long) { return Row{0}; }
+    __device__ static __forceinline__ const char* stream(const Params& p, long long, int i) {
+        if (i == 0) return reinterpret_cast<const char*>(p.pred_x);
+        if (i == 1) return reinterpret_cast<const char*>(p.pred_a);
+        if (i == 2) return reinterpret_cast<const char*>(p.tgt_x);
+        return reinterpret_cast<const char*>(p.tgt_a);
+    }
+    __device__ static __forceinline__ void unit(const Params& p, const Row&, const uint4 (&in)[NIN][2],
+                                                long long unit_index, float (&acc)[2]) {
+        float px[W], pa[W], tx[W], ta[W], gx[W], ga[W];
+        decode_pred<TP, W>(in[0], px);
+        decode_pred<TP, W>(in[1], pa);
+        decode_pred<TT, W>(in[2], tx);
+        if constexpr (!SHARED_TGT) decode_pred<TT, W>(in[3], ta);
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const float ux = __fsub_rn(px[q], tx[q]);
+            const float ua = __fsub_rn(pa[q], SHARED_TGT ? tx[q] : ta[q]);
+            acc[0] = fmaf(ux, ux, acc[0]);
+            acc[1] = fmaf(ua, ua, acc[1]);
+            gx[q] = __fmul_rn(p.go_x, __fmul_rn(2.0f, ux));
+            ga[q] = __fmul_rn(p.go_a, __fmul_rn(2.0f, ua));
+        }
+        store_pred<TP, W>(p.grad_x + unit_index * W, gx);
+        store_pred<TP, W>(p.grad_a + unit_index * W, ga);
+    }
+    __device__ static __forceinline__ void row_end(const Params& p, const Row&, long long row, const double (&tot)[2]) {
+        p.row_loss_x[row] = (float)tot[0];
+        p.row_loss_a[row] = (float)tot[1];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
 template <typename TP, typename T>
@@ -454,6 +594,12 @@ static int launch_wmse_fwd_bwd(const void* pred, const void* x_mix, const void* 
                                void* workspace, long long B, long long D, cudaStream_t st) {
     constexpr int W = VecTraits<T>::N;
     RowWorkspace ws = carve_row_workspace(workspace, B);
+    if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a) && use_tma_pipeline()) {
+        using Op = WmseFwdBwdOp<TP, T>;
+        typename Op::Params p{(const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps,
+                              w_x, w_a, go_x, go_a, (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a};
+        return launch_pipe<Op>(p, ws, B, D, W, st);
+    }
     if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a)) {
         RowSched rt = make_row_sched(B, D, W, kK3Occ);
         wmse_fwd_bwd_kernel<TP, T, W, true><<<rt.grid, kThreads, 0, st>>>(
@@ -522,6 +668,18 @@ static int launch_dual_mse(const void* pred_x, const void* pred_a, const void* t
     RowWorkspace ws = carve_row_workspace(workspace, B);
     const bool vec = (D % W == 0) && aligned16(pred_x) && aligned16(pred_a) && aligned16(tgt_x) &&
                      aligned16(tgt_a) && aligned16(grad_x) && aligned16(grad_a);
+    if (vec && use_tma_pipeline()) {
+        if (tgt_a == tgt_x) {
+            using Op = DualMseOp<TP, TT, true>;
+            typename Op::Params p{(const TP*)pred_x, (const TP*)pred_a, (const TT*)tgt_x, (const TT*)tgt_a, go_x, go_a,
+                                  (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a};
+            return launch_pipe<Op>(p, ws, B, D, W, st);
+        }
+        using Op = DualMseOp<TP, TT, false>;
+        typename Op::Params p{(const TP*)pred_x, (const TP*)pred_a, (const TT*)tgt_x, (const TT*)tgt_a, go_x, go_a,
+                              (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a};
+        return launch_pipe<Op>(p, ws, B, D, W, st);
+    }
     if (vec) {
         RowSched rt = make_row_sched(B, D, W, kK3Occ);
         dual_mse_kernel<TP, TT, W, true><<<rt.grid, kThreads, 0, st>>>(

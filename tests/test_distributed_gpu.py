@@ -1,0 +1,85 @@
+"""GPU, world_size 2, NCCL: UnlearnStep + GradCombiner with the real kernels on two B200s must equal
+the single-GPU run on the concatenated batch. Skipped when fewer than 2 GPUs."""
+import os
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+pytestmark = pytest.mark.gpu
+
+
+class TinyNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(5)
+        self.c1 = torch.nn.Conv2d(1, 4, 3, padding=1)
+        self.c2 = torch.nn.Conv2d(4, 1, 3, padding=1)
+        self.odd = torch.nn.Parameter(torch.zeros(3))
+
+    def forward(self, x, timesteps, return_dict=False, **kw):
+        return (self.c2(torch.tanh(self.c1(x))) + self.odd.sum(),)
+
+
+def _batch(Bg):
+    g = torch.Generator().manual_seed(321)
+    return (torch.rand(Bg, 1, 16, 16, generator=g) * 2 - 1, torch.rand(Bg, 1, 16, 16, generator=g) * 2 - 1,
+            torch.randn(Bg, 1, 16, 16, generator=g), torch.randint(300, 1000, (Bg,), generator=g))
+
+
+def _run(rank, world, Bg, G):
+    from siss_b200 import parallel
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda", rank if world > 1 else 0)
+    net = TinyNet().to(dev)
+    comb = GradCombiner(net.parameters())
+    step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
+                       train_batch_size=Bg, gradient_accumulation_steps=G, lambd=0.5, scaling_norm=5.0, max_norm=1.0)
+    torch.manual_seed(17)
+    for k in range(G):
+        x0, a0, noise, t = _batch(Bg)
+        keep = parallel.global_keep_mask(Bg, 0.5, rank, world)
+        sh = lambda v: parallel.shard_rows(v, rank, world).to(dev)
+        step.micro_step(sh(x0 + 0.01 * k), sh(a0), sh(noise), sh(t), keep_mask=keep)
+    stats = step.sync_step()
+    torch.cuda.synchronize()
+    return torch.cat([p.grad.reshape(-1) for p in net.parameters()]).cpu(), stats.cpu()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from siss_b200 import parallel
+    parallel.init_from_env("nccl")
+    flat, stats = _run(rank, world, 8, 2)
+    if rank == 0:
+        q.put((flat, stats))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_step_equals_single_gpu():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat2, stats2 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    flat1, stats1 = _run(0, 1, 8, 2)
+    torch.testing.assert_close(flat2, flat1, rtol=2e-4, atol=2e-6)
+    torch.testing.assert_close(stats2, stats1, rtol=2e-4, atol=1e-7)
