@@ -36,6 +36,15 @@ if str(ROOT) not in sys.path:
 
 import torch  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "SISS loss+grad-combine samples/s"
 UNIT = "samples/s"
 CELEB_PARAMS = 113_673_219  # google/ddpm-celebahq-256 UNet2DModel parameter count
@@ -55,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--transport", choices=["auto", "p2p", "nccl"], default="auto",
+                    help="N>1 gradient exchange: fused NVLink peer-memory kernels or NCCL collectives")
     return ap.parse_args()
 
 
@@ -209,7 +220,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n):
@@ -218,7 +229,7 @@ def workload_config(args, n):
         "per_gpu_batch": args.batch, "global_batch": args.batch * n, "shape": [args.channels, args.res, args.res],
         "latent_dtype": args.dtype, "pred_dtype": "fp32", "timesteps": "t=999 (delete_celeb.py:593)",
         "grad_params": args.params, "grad_accum": 1, "unet": "outside the path (resident eps_hat / P-param stub in e2e)",
-        "parallelism": f"dp{n}", "l2": "inputs larger than L2 (per-step footprint >> 126 MB); no flush",
+        "parallelism": f"dp{n}", "transport": getattr(args, "_transport", "single" if n == 1 else "nccl"), "l2": "inputs larger than L2 (per-step footprint >> 126 MB); no flush",
         "resident_step": "K1oK2 + K3 + K4a + K4b (+ reduce-scatter x2, scalar all-reduce, all-gather when N>1)",
     }
 
@@ -293,8 +304,24 @@ def run_siss(args):
     keep = (torch.rand(B, generator=torch.Generator().manual_seed(7)) > lambd).to(torch.uint8).to(dev)
     pad = 4 * n
     Ptot = (P + pad - 1) // pad * pad
-    G_x = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
-    G_a = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
+    peer = None
+    transport = "single" if n == 1 else "nccl"
+    if n > 1 and args.transport in ("auto", "p2p"):
+        try:
+            from siss_b200.p2p import PeerExchange
+            peer = PeerExchange(Ptot, dev)
+            transport = "p2p"
+        except Exception as e:  # symmetric memory not available: NCCL collectives
+            if args.transport == "p2p":
+                raise
+            print(f"[bench] peer-memory transport unavailable: {e!r}", file=sys.stderr)
+    if peer is not None:
+        G_x, G_a = peer.g_x, peer.g_a
+        G_x.copy_(torch.randn(Ptot, generator=gen, device=dev) * 1e-3)
+        G_a.copy_(torch.randn(Ptot, generator=gen, device=dev) * 1e-3)
+    else:
+        G_x = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
+        G_a = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
     G_out = torch.empty_like(G_x)
     sums = torch.zeros(3, dtype=torch.float64, device=dev)
     stats5 = torch.zeros(5, device=dev)
@@ -302,7 +329,10 @@ def run_siss(args):
         S = Ptot // n
         sh_x, sh_a = torch.empty(S, device=dev), torch.empty(S, device=dev)
 
-    kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_norm3", "siss_combine"]
+    if peer is not None:
+        kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_p2p_exchange_combine"]
+    else:
+        kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_norm3", "siss_combine"]
     evs = {k: [] for k in kernels}
 
     def timed(name, record, fn):
@@ -323,6 +353,10 @@ def run_siss(args):
             timed("siss_norm3", record, lambda: ops.norm3(G_x, G_a, out=sums))
             timed("siss_combine", record, lambda: ops.combine(G_x, G_a, sums, _lib.SISS_COMBINE_SCALING_NORM,
                                                               scaling_norm, max_norm, out=G_out, stats=stats5))
+        elif peer is not None:
+            # fused: barrier | reduce-scatter x2 + K4a over peer loads | barrier | K4b + all-gather over peer stores | barrier
+            timed("siss_p2p_exchange_combine", record, lambda: peer.combine(_lib.SISS_COMBINE_SCALING_NORM, scaling_norm,
+                                                                           max_norm, False, stats5))
         else:
             dist.reduce_scatter_tensor(sh_x, G_x)
             dist.reduce_scatter_tensor(sh_a, G_a)
@@ -332,6 +366,7 @@ def run_siss(args):
                                                               scaling_norm, max_norm, out=sh_x, stats=stats5))
             dist.all_gather_into_tensor(G_out, sh_x)
 
+    args._transport = transport
     for _ in range(max(args.warmup, 3)):
         resident_step()
     barrier()
@@ -361,6 +396,8 @@ def run_siss(args):
         "siss_wmse_fwd_bwd": (12 + 3 * s_in) * B * D,
         "siss_norm3": 8 * Pk,
         "siss_combine": 12 * Pk,
+        # NVLink bytes per rank: (N-1)/N * (8 in + 4 out) B/param; reported against HBM peak only for reference
+        "siss_p2p_exchange_combine": 12 * (Ptot - Pk),
     }
     peak, peak_src = load_peaks()
     per_kernel = {k: {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "gbs": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9,
@@ -377,7 +414,10 @@ def run_siss(args):
         del G_out, pred
         torch.cuda.empty_cache()
         unet = BenchUNet(P).to(dev)
-        comb = GradCombiner(unet.parameters())
+        del G_x, G_a
+        peer = None
+        torch.cuda.empty_cache()
+        comb = GradCombiner(unet.parameters(), transport=args.transport)
         step = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B * n,
                            lambd=lambd, scaling_norm=scaling_norm, max_norm=max_norm)
         x0_p, a0_p = x0_h.pin_memory(), a0_h.pin_memory()
@@ -391,9 +431,10 @@ def run_siss(args):
             nz = torch.randn(shape, dtype=dt, device=dev)     # :581
             ts = torch.randint(999, 1000, (B,), device=dev).long()   # :593
             out = step.micro_step(x0, a0, nz, ts)             # CPU Bernoulli draw + 64 B H2D inside
-            bs = batch_stats(out, D)                          # :626-656 from the O(B) row sums
+            bs = batch_stats(out, D)                          # :626-656 from the O(B) row sums (one launch)
             st = step.sync_step()
-            host_out.copy_(torch.cat([st, torch.stack(list(bs.values()))]), non_blocking=True)
+            host_out[:5].copy_(st, non_blocking=True)
+            host_out[5:].copy_(bs, non_blocking=True)
             done.record()
             done.synchronize()                                # the loop reads its metrics every step
             return host_out
@@ -436,13 +477,19 @@ def run_siss(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: anything native libraries (NCCL banner, ...) write to fd 1
+    # goes to stderr instead; the line itself is written to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

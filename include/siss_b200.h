@@ -207,6 +207,49 @@ int siss_combine(const float* g_x, const float* g_a, float* out, int64_t n,
                  const double* sums3, int mode, float value, float max_norm, int inf_guard,
                  float* stats5, siss_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused statistics epilogue — the per-batch logging scalars of delete_celeb.py:626-656 (mean over
+ * all elements; max / min / unbiased std of the per-sample means; mean / max / min / std of the
+ * importance weights) in one launch from the O(B) per-sample sums of K2/K3.
+ * out16 = [loss_x: mean,max,min,std | loss_a: ... | importance_weight_x: ... | importance_weight_a: ...].
+ * Any input may be NULL (its four outputs are NaN). row_loss_* are per-sample SUMS over D elements.
+ * ---------------------------------------------------------------------------------------- */
+int siss_batch_stats(const float* row_loss_x, const float* row_loss_a, const float* w_x, const float* w_a,
+                     int64_t B, int64_t D, float* out16, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel exchange fused with K4 over NVLink peer memory (one process per GPU, 2/4/8 GPUs of
+ * one NVSwitch box). Replaces what DDP's bucketed all-reduce does implicitly inside
+ * `accelerator.backward` on the sync step (delete_celeb.py:691) — and also reduces the NegGrad term,
+ * which the reference never does.
+ * `h_*` parameters are HOST arrays of `world` DEVICE pointers, one per rank, all mapped into this
+ * process (CUDA IPC / symmetric memory). The caller must barrier all ranks on the stream before the
+ * first kernel (every rank's G_x, G_a complete), between the two (every rank's scalar slot written)
+ * and after the second (every rank's output complete).
+ *
+ * siss_p2p_reduce_norm3: reduce-scatter(G_x) + reduce-scatter(G_a) + K4a in one kernel. Rank `rank`
+ * reads elements [rank*shard_len, (rank+1)*shard_len) of every peer's buffers, sums them in rank
+ * order, writes the reduced shard to shard_x / shard_a (local), writes this rank's three partial sums
+ * to sums3_local and to doubles [4*rank .. 4*rank+2] of every peer's scalar buffer h_peer_scalars[r]
+ * (each at least 4*world doubles). Inbound NVLink bytes per rank: (world-1)/world * 8 per parameter.
+ *
+ * siss_p2p_combine_allgather: K4b + all-gather in one kernel. Sums the `world` scalar slots (local
+ * copy, rank order, so every rank derives identical s and clip), computes
+ * clip * (shard_x - s * shard_a) and stores it to elements [rank*shard_len, ...) of EVERY peer's
+ * h_peers_out[r]. Outbound NVLink bytes per rank: (world-1)/world * 4 per parameter.
+ * ---------------------------------------------------------------------------------------- */
+int64_t siss_p2p_workspace_bytes(void);
+
+int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_peers_a,
+                          double* const* h_peer_scalars, int world, int rank, int64_t shard_len,
+                          float* shard_x, float* shard_a, double* sums3_local,
+                          void* workspace, siss_stream_t stream);
+
+int siss_p2p_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                               float* const* h_peers_out, int world, int rank, int64_t shard_len,
+                               int mode, float value, float max_norm, int inf_guard, float* stats5,
+                               siss_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 // synchronisation between them (an NCCL all-reduce of the three doubles can sit in between).
 
 #include "common.cuh"
+#include "combine_scalars.cuh"
 
 namespace siss {
 
@@ -104,46 +105,11 @@ norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long lo
     }
 }
 
-struct CombineScalars {
-    float s;     // scaling factor
-    float clip;  // clip coefficient (<= 1)
-};
-
-// Scalar prologue shared by every thread of K4b; fp32 op order of the reference.
+// scalar prologue of K4b: combine_scalars.cuh (shared with the peer-memory variant in p2p.cu)
 __device__ __forceinline__ CombineScalars combine_scalars(const double* __restrict__ sums3, int mode, float value,
                                                           float max_norm, int inf_guard, float* stats5,
                                                           bool write_stats) {
-    const double sxx = sums3[0], saa = sums3[1], sxa = sums3[2];
-    const float n_x = sqrtf((float)sxx);  // torch.sqrt(sum of per-tensor norm**2), delete_celeb.py:733-734
-    const float n_a = sqrtf((float)saa);
-    float s;
-    if (mode == SISS_COMBINE_NONE) {
-        s = 0.0f;
-    } else if (mode == SISS_COMBINE_ERASEDIFF) {
-        // eta - <g_x,g_a> / ||g_a||**2 ; -max(., 0)      delete_celeb.py:741-742
-        float sf = __fsub_rn(value, __fdiv_rn((float)sxa, __fmul_rn(n_a, n_a)));
-        sf = (0.0f > sf) ? 0.0f : sf;  // python max(sf, 0): keeps NaN
-        s = -sf;
-    } else {
-        s = __fdiv_rn(value, n_a);     // scaling_norm / ||g_a||   delete_celeb.py:746
-        if (inf_guard && isinf(s)) s = 0.0f;  // delete_tshirt.py:688-690
-    }
-    // ||g_x - s g_a||^2 from the three sums, in fp64
-    const double sd = (double)s;
-    double tn2 = sxx - 2.0 * sd * sxa + sd * sd * saa;
-    if (tn2 < 0.0) tn2 = 0.0;
-    const float tn = (float)sqrt(tn2);
-    float clip = 1.0f;
-    if (max_norm > 0.0f) {
-        // torch.nn.utils.clip_grad_norm_: max_norm / (total_norm + 1e-6), clamped to 1
-        clip = __fdiv_rn(max_norm, __fadd_rn(tn, 1e-6f));
-        clip = (clip > 1.0f) ? 1.0f : clip;
-    }
-    if (write_stats && stats5) {
-        stats5[0] = n_x; stats5[1] = n_a; stats5[2] = s; stats5[3] = tn; stats5[4] = clip;
-    }
-    CombineScalars r; r.s = s; r.clip = clip;
-    return r;
+    return combine_scalars_from(sums3[0], sums3[1], sums3[2], mode, value, max_norm, inf_guard, stats5, write_stats);
 }
 
 __global__ void __launch_bounds__(kThreads, kK4Occ)

@@ -37,7 +37,11 @@ _ALIGN = 4  # parameters start on 16-byte boundaries inside the flat buffers
 
 class GradCombiner:
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group: Optional[dist.ProcessGroup] = None,
-                 distributed: Optional[bool] = None):
+                 distributed: Optional[bool] = None, transport: str = "auto"):
+        """``transport`` selects how the data-parallel exchange is carried when world > 1:
+        ``"p2p"``  fused peer-memory kernels over NVLink (siss_b200/p2p.py, csrc/p2p.cu);
+        ``"nccl"`` torch.distributed collectives around K4a/K4b;
+        ``"auto"`` p2p on CUDA with 2/4/8 ranks when symmetric memory can be set up, else nccl."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradCombiner needs at least one parameter that requires grad")
@@ -63,16 +67,36 @@ class GradCombiner:
         self.num_params = sum(p.numel() for p in self.params)
         quantum = _ALIGN * self.world
         self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's shard is 16B aligned
-        self.g_x = torch.zeros(self.total, dtype=torch.float32, device=dev)
-        self.g_a = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.peer = None
+        if transport not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"unknown transport {transport!r}")
+        if self.world > 1 and transport in ("auto", "p2p") and dev.type == "cuda":
+            try:
+                from .p2p import PeerExchange
+                self.peer = PeerExchange(self.total, dev, process_group)
+            except Exception as e:
+                if transport == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"siss_b200: peer-memory transport unavailable ({e!r}); using NCCL collectives")
+                self.peer = None
+        if self.peer is not None:
+            self.g_x, self.g_a = self.peer.g_x, self.peer.g_a
+        else:
+            self.g_x = torch.zeros(self.total, dtype=torch.float32, device=dev)
+            self.g_a = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.transport = "single" if self.world == 1 else ("p2p" if self.peer is not None else "nccl")
         self._views_x = [self.g_x[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
         self._views_a = [self.g_a[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
         self.sums3 = torch.zeros(3, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(5, dtype=torch.float32, device=dev)
         if self.world > 1:
             self.shard_len = self.total // self.world
-            self._shard_x = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
-            self._shard_a = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
+            if self.peer is not None:
+                self._shard_x, self._shard_a = self.peer.shard_x, self.peer.shard_a
+            else:
+                self._shard_x = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
+                self._shard_a = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
         self._dirty_x = False  # G_x holds the previous combined gradient and must be cleared
         # compute back-ends: the CUDA kernels. (tests of the collective choreography on gloo/CPU
         # replace these two attributes with the oracle; the product has no other path.)
@@ -112,6 +136,8 @@ class GradCombiner:
         if self.world == 1:
             self._norm3(self.g_x, self.g_a, out=self.sums3)
             self._combine(self.g_x, self.g_a, self.sums3, mode, value, mn, inf_guard, out=self.g_x, stats=self.stats)
+        elif self.peer is not None:
+            self.peer.combine(mode, value, mn, inf_guard, self.stats)
         else:
             dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
             dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)

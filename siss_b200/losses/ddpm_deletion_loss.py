@@ -138,3 +138,33 @@ class DDPMDeletionLoss:
         loss_x = _SqErr.apply(all_noise_preds, noise)
         loss = loss_x
         return loss, loss_x, None, None, None, None, None
+
+    # ---- Reviewer-proposed loss (only the tshirt task honours it, delete_tshirt.py:632) -------------
+    def subscore_bernoulli(self, unet, timesteps, noise, conditioning, all_samples_dict, deletion_samples_dict,
+                           lambd, keep_mask=None):
+        """ddpm_deletion_loss.py:99-122. Same Bernoulli row select as SISS (K2's select), one forward,
+        plain squared error against the shared noise (the sqerr kernel), then the reference's ragged split
+        by mask with the 1/(1-lambd) factor on the keep rows. The boolean-mask gathers are torch indexing:
+        the outputs are ragged, there is nothing to fuse. lambd == 1 raises ZeroDivisionError exactly like
+        the reference (Python-level 1 / (1 - lambd))."""
+        noisy_x = all_samples_dict['noisy_latents']
+        noisy_a = deletion_samples_dict['noisy_latents']
+        batch_size = noisy_x.shape[0]
+        all_mask = _draw_keep_mask(batch_size, lambd) if keep_mask is None else keep_mask
+        deletion_mask = ~all_mask
+        bernoulli_samples, *_ = ops.mixture_weights(
+            noisy_x, noisy_a, all_samples_dict['og_latents'], deletion_samples_dict['og_latents'], all_mask,
+            timesteps, self.all_gamma, self.all_sigma, lambd)
+        noise_preds = unet(bernoulli_samples, timesteps, **conditioning, return_dict=False)[0]
+        loss = _SqErr.apply(noise_preds, noise)
+        dev_all, dev_del = all_mask.to(loss.device), deletion_mask.to(loss.device)
+        loss_x = (1 / (1 - lambd)) * loss[dev_all]
+        loss_a = loss[dev_del]
+        if len(loss_x) == 0:
+            print('no nondeletion samples')
+            loss_x = torch.zeros(1, 1, 1, 1, requires_grad=True, device=loss.device)
+            loss_a = torch.zeros(1, 1, 1, 1, requires_grad=True, device=loss.device)
+        if len(loss_a) == 0:
+            print('no deletion samples')
+            loss_a = torch.zeros(1, 1, 1, 1, requires_grad=True, device=loss.device)
+        return None, loss_x, loss_a, None, None, loss_x, loss_a

@@ -388,3 +388,30 @@ def combine(g_x: torch.Tensor, g_a: torch.Tensor, sums3: torch.Tensor, mode: int
                                         int(bool(inf_guard)), _ptr(stats), _stream()), "siss_combine")
     _count()
     return out, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# fused statistics epilogue
+# ------------------------------------------------------------------------------------------------
+STAT_KEYS = tuple(f"{q}/{s}" for q in ("loss_x", "loss_a", "importance_weight_x", "importance_weight_a")
+                  for s in ("mean", "max", "min", "std"))
+
+
+def batch_stats(row_loss_x: Optional[torch.Tensor], row_loss_a: Optional[torch.Tensor], w_x: Optional[torch.Tensor],
+                w_a: Optional[torch.Tensor], elems_per_sample: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The 16 logging scalars of delete_celeb.py:626-656 in one launch (order: ``STAT_KEYS``).
+    Inputs are the per-sample sums / weights K2 and K3 return; any may be None (-> NaN outputs)."""
+    present = [t for t in (row_loss_x, row_loss_a, w_x, w_a) if t is not None]
+    if not present:
+        raise ValueError("batch_stats needs at least one input")
+    dev = _need_cuda(*present)
+    B = present[0].numel()
+    for t in present:
+        if t.dtype != torch.float32 or t.numel() != B or not t.is_contiguous():
+            raise ValueError("batch_stats inputs must be contiguous float32 vectors of one length")
+    if out is None:
+        out = torch.empty(16, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().siss_batch_stats(_ptr(row_loss_x), _ptr(row_loss_a), _ptr(w_x), _ptr(w_a), B,
+                                            int(elems_per_sample), _ptr(out), _stream()), "siss_batch_stats")
+    _count()
+    return out

@@ -142,26 +142,58 @@ class UnlearnStep:
         return self._micro >= self.G
 
 
-def batch_stats(out: Dict[str, torch.Tensor], elems_per_sample: int) -> Dict[str, torch.Tensor]:
-    """The reference's per-batch statistics (delete_celeb.py:626-656) from the O(B) row sums — device
-    scalars, no host sync. mean over all elements == mean of per-sample means (equal row sizes)."""
-    stats: Dict[str, torch.Tensor] = {}
-    for name in ("loss_x", "loss_a"):
-        rows = out.get(f"row_{name}")
-        if rows is None:
-            continue
-        per = rows / elems_per_sample
-        stats[f"{name}/mean"] = per.mean()
-        stats[f"{name}/max"] = per.max()
-        stats[f"{name}/min"] = per.min()
-        stats[f"{name}/std"] = per.std() if per.numel() > 1 else per.new_full((), float("nan"))
-    for name in ("w_x", "w_a"):
-        w = out.get(name)
-        if w is None:
-            continue
-        key = "importance_weight_" + name[-1]
-        stats[f"{key}/mean"] = w.mean()
-        stats[f"{key}/max"] = w.max()
-        stats[f"{key}/min"] = w.min()
-        stats[f"{key}/std"] = w.std() if w.numel() > 1 else w.new_full((), float("nan"))
-    return stats
+def batch_stats(out: Dict[str, torch.Tensor], elems_per_sample: int,
+                dest: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The reference's per-batch statistics (delete_celeb.py:626-656) from the O(B) row sums of
+    ``micro_step`` — ONE kernel launch (``siss_batch_stats``), 16 fp32 scalars on the device in the order
+    of ``siss_b200.ops.STAT_KEYS``; no host synchronisation (the reference does ~20 ``.item()`` here)."""
+    return ops.batch_stats(out.get("row_loss_x"), out.get("row_loss_a"), out.get("w_x"), out.get("w_a"),
+                           elems_per_sample, out=dest)
+
+
+class StepLog:
+    """Sync-free logging: one small pinned-host record per step.
+
+    ``push(stats16, grad_stats5)`` enqueues a non-blocking device->host copy of the 21 scalars into a ring
+    of pinned buffers and records an event; ``pop_ready()`` returns the records whose copies have
+    completed, as dicts keyed like the reference's ``batch_stats`` / wandb scalars — the training loop
+    never waits for the GPU in order to log."""
+
+    GRAD_KEYS = ("gradient/norm_loss_x", "gradient/norm_loss_a", "gradient/scaling_factor", "gradient/total_norm",
+                 "gradient/clip_coef")
+
+    def __init__(self, depth: int = 8):
+        self._bufs = [torch.empty(21, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self._events = [torch.cuda.Event() for _ in range(depth)]
+        self._pending = []   # (slot, step)
+        self._next = 0
+
+    def push(self, stats16: Optional[torch.Tensor], grad_stats5: Optional[torch.Tensor], step: int = 0) -> None:
+        slot = self._next % len(self._bufs)
+        if any(sl == slot for sl, _ in self._pending):
+            self._events[slot].synchronize()          # ring full: wait for the oldest record only
+        buf = self._bufs[slot]
+        buf.fill_(float("nan"))
+        if stats16 is not None:
+            buf[:16].copy_(stats16, non_blocking=True)
+        if grad_stats5 is not None:
+            buf[16:].copy_(grad_stats5, non_blocking=True)
+        self._events[slot].record()
+        self._pending = [(sl, st) for sl, st in self._pending if sl != slot] + [(slot, step)]
+        self._next += 1
+
+    def pop_ready(self, wait: bool = False):
+        done, keep = [], []
+        for slot, step in self._pending:
+            if wait:
+                self._events[slot].synchronize()
+            if self._events[slot].query():
+                vals = self._bufs[slot].tolist()
+                rec = dict(zip(ops.STAT_KEYS, vals[:16]))
+                rec.update(zip(self.GRAD_KEYS, vals[16:]))
+                rec["step"] = step
+                done.append(rec)
+            else:
+                keep.append((slot, step))
+        self._pending = keep
+        return done

@@ -226,3 +226,54 @@ def test_drop_in_loop_with_grad_combiner(dev):
         torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-4, atol=2e-6)
     st = comb.stats_dict()
     assert set(st) >= {"gradient/norm_loss_x", "gradient/norm_loss_a", "gradient/scaling_factor"}
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_subscore_bernoulli_matches_reference(name, dev):
+    """§8(f)3: the reviewer-proposed loss, against the reference's own outputs (bit-exact: select + sqerr)."""
+    from siss_b200.losses import DDPMDeletionLoss
+    c = load_golden(name)
+    loss = DDPMDeletionLoss(gamma=c["gamma"].to(dev), sigma=c["sigma"].to(dev))
+    all_d = _to({"og_latents": c["x0"], "noisy_latents": c["xt_x"]}, dev)
+    del_d = _to({"og_latents": c["a0"], "noisy_latents": c["xt_a"]}, dev)
+    torch.manual_seed(c["subscore_seed"])
+    args = (O.StubUNet().to(dev), c["t"].to(dev), c["noise"].to(dev), _to(conditioning_of(c), dev), all_d, del_d)
+    if "subscore_raises" in c:
+        with pytest.raises(ZeroDivisionError):
+            loss.subscore_bernoulli(*args, lambd=c["lambd"])
+        return
+    it = loss.subscore_bernoulli(*args, lambd=c["lambd"])
+    assert it[0] is None and it[3] is None and it[4] is None and it[5] is it[1] and it[6] is it[2]
+    assert it[1].shape == c["subscore_loss_x"].shape and it[2].shape == c["subscore_loss_a"].shape
+    assert torch.equal(it[1].detach().cpu(), c["subscore_loss_x"])
+    assert torch.equal(it[2].detach().cpu(), c["subscore_loss_a"])
+    if it[1].numel() > 1 and it[1].requires_grad:
+        (it[5].sum() / 4).backward(retain_graph=True)     # the tshirt loop keeps the graph for this method too
+        (it[6].sum() / 4).backward()
+
+
+@pytest.mark.parametrize("name", ["tshirt_fp32", "celeb_bf16_t999", "celeb_fp32_t999", "fp16_mid_t", "odd_D_fp32"])
+def test_fused_batch_stats_match_reference_stats_block(name, dev):
+    """§8(f)1: the 16 logging scalars (delete_celeb.py:626-656) from the O(B) row sums vs the same
+    statistics computed the reference's way on the full [B,C,H,W] tensors of the golden fixture."""
+    from siss_b200 import ops
+    from siss_b200.step import StepLog, batch_stats
+    c = load_golden(name)
+    items = (None, c["siss_loss_x"], c["siss_loss_a"], c["siss_w_x"], c["siss_w_a"], None, None)
+    ref = O.batch_stats(items)
+    D = c["x0"][0].numel()
+    out = {"row_loss_x": c["siss_loss_x"].sum(dim=[1, 2, 3]).to(dev), "row_loss_a": c["siss_loss_a"].sum(dim=[1, 2, 3]).to(dev),
+           "w_x": c["siss_w_x"].to(dev), "w_a": c["siss_w_a"].to(dev)}
+    got = dict(zip(ops.STAT_KEYS, batch_stats(out, D).tolist()))
+    for k, v in ref.items():
+        assert got[k] == pytest.approx(v, rel=2e-5, abs=1e-30), k
+    # missing inputs -> NaN block; B == 1 -> std NaN like torch.std
+    part = ops.batch_stats(out["row_loss_x"][:1].contiguous(), None, None, None, D).tolist()
+    assert part[0] == pytest.approx(float(out["row_loss_x"][0]) / D, rel=1e-6) and part[3] != part[3] and part[4] != part[4]
+    # sync-free logging record
+    log = StepLog(depth=2)
+    for step in range(3):
+        log.push(batch_stats(out, D), torch.arange(5, dtype=torch.float32, device=dev), step)
+    recs = log.pop_ready(wait=True)
+    assert [r["step"] for r in recs] == [1, 2] and recs[-1]["gradient/scaling_factor"] == 2.0
+    assert recs[-1]["loss_x/mean"] == pytest.approx(ref["loss_x/mean"], rel=2e-5)

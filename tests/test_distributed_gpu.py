@@ -32,7 +32,7 @@ def _batch(Bg):
             torch.randn(Bg, 1, 16, 16, generator=g), torch.randint(300, 1000, (Bg,), generator=g))
 
 
-def _run(rank, world, Bg, G):
+def _run(rank, world, Bg, G, transport="auto"):
     from siss_b200 import parallel
     from siss_b200.grad_combine import GradCombiner
     from siss_b200.scheduler import SissDDPMScheduler
@@ -40,7 +40,9 @@ def _run(rank, world, Bg, G):
     torch.backends.cudnn.allow_tf32 = False
     dev = torch.device("cuda", rank if world > 1 else 0)
     net = TinyNet().to(dev)
-    comb = GradCombiner(net.parameters())
+    comb = GradCombiner(net.parameters(), transport=transport)
+    if world > 1 and transport != "auto":
+        assert comb.transport == transport
     step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
                        train_batch_size=Bg, gradient_accumulation_steps=G, lambd=0.5, scaling_norm=5.0, max_norm=1.0)
     torch.manual_seed(17)
@@ -60,9 +62,11 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     from siss_b200 import parallel
     parallel.init_from_env("nccl")
-    flat, stats = _run(rank, world, 8, 2)
+    out = {}
+    for transport in ("nccl", "p2p"):
+        out[transport] = _run(rank, world, 8, 2, transport)
     if rank == 0:
-        q.put((flat, stats))
+        q.put(out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,10 +80,11 @@ def test_two_gpu_step_equals_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    flat2, stats2 = q.get(timeout=300)
+    out = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     flat1, stats1 = _run(0, 1, 8, 2)
-    torch.testing.assert_close(flat2, flat1, rtol=2e-4, atol=2e-6)
-    torch.testing.assert_close(stats2, stats1, rtol=2e-4, atol=1e-7)
+    for transport, (flat2, stats2) in out.items():      # NCCL collectives and fused NVLink peer-memory kernels
+        torch.testing.assert_close(flat2, flat1, rtol=2e-4, atol=2e-6, msg=lambda m: f"{transport}: {m}")
+        torch.testing.assert_close(stats2, stats1, rtol=2e-4, atol=1e-7, msg=lambda m: f"{transport}: {m}")
