@@ -208,6 +208,22 @@ int siss_combine(const float* g_x, const float* g_a, float* out, int64_t n,
                  float* stats5, siss_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4b fused with the optimiser step: g = clip * (g_x - s * g_a) is consumed in registers by a
+ * torch.optim.AdamW update (decoupled weight decay; config/delete_celeb.yaml:127-134, stepped at
+ * delete_celeb.py:769) of the flat fp32 parameter buffer `param` and its moments; with zero_grads the
+ * two gradient buffers are cleared in the same pass (replaces optimizer.zero_grad(), :773).
+ *   sums3 == NULL        : no combine scalars — g = g_x (already combined / exchanged), no clip;
+ *   mode == SISS_COMBINE_NONE : single-term methods, g = clip * g_x (g_a may be NULL);
+ *   grad_out (nullable)  : also materialise g (may alias g_x), e.g. for logging or a later hook;
+ *   step                 : 1-based optimiser step count (bias corrections 1 - beta^step).
+ * 40 bytes/parameter (5 reads + 5 writes) instead of 48 in 4 launches for K4b + AdamW + 2 memsets.
+ * ---------------------------------------------------------------------------------------- */
+int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const double* sums3, int mode, float value,
+                       float max_norm, int inf_guard, float* param, float* exp_avg, float* exp_avg_sq,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                       int zero_grads, float* grad_out, float* stats5, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused statistics epilogue — the per-batch logging scalars of delete_celeb.py:626-656 (mean over
  * all elements; max / min / unbiased std of the per-sample means; mean / max / min / std of the
  * importance weights) in one launch from the O(B) per-sample sums of K2/K3.

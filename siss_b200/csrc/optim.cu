@@ -1,0 +1,156 @@
+// K4b fused with the optimiser step: the combined, clipped gradient
+//     g = clip * (G_x - s * G_a)
+// is consumed in registers by a decoupled-weight-decay Adam update of the flat fp32 parameter buffer
+// (torch.optim.AdamW as configured at config/delete_celeb.yaml:127-134, stepped at delete_celeb.py:769)
+// and G_x / G_a are cleared in the same pass, so `optimizer.zero_grad()` (:773) and the two memsets of
+// the unfused path disappear too:
+//     unfused: K4b 12 + AdamW 28 + 2 memsets 8 = 48 B/param, 4 launches
+//     fused  : read G_x G_a p m v (20) + write p m v G_x G_a (20) = 40 B/param, 1 launch
+// Update rule, in torch's single-tensor op order (fp32):
+//     p *= 1 - lr*wd ; m += (1-b1) (g - m) ; v = v*b2 + (1-b2) g g
+//     p += (-lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+
+#include "common.cuh"
+#include "combine_scalars.cuh"
+
+namespace siss {
+
+int cached_sm_count();
+
+constexpr int kOptOcc = 3;
+constexpr int kOptUnroll = 2;
+
+struct AdamScalars {
+    float decay;        // 1 - lr * weight_decay
+    float w1;           // 1 - beta1
+    float beta2;
+    float w2;           // 1 - beta2
+    float bc2_sqrt;     // sqrt(1 - beta2^t)
+    float neg_step;     // -lr / (1 - beta1^t)
+    float eps;
+};
+
+__device__ __forceinline__ void adam_update(float g, float& p, float& m, float& v, const AdamScalars& a) {
+    p = __fmul_rn(p, a.decay);
+    m = __fadd_rn(m, __fmul_rn(a.w1, __fsub_rn(g, m)));                        // lerp, small weight branch
+    v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(a.w2, g), g));    // mul_ ; addcmul_
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), a.bc2_sqrt), a.eps);
+    p = __fadd_rn(p, __fmul_rn(a.neg_step, __fdiv_rn(m, denom)));              // addcdiv_
+}
+
+template <bool TWO_TERM>
+__global__ void __launch_bounds__(kThreads, kOptOcc)
+combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n, long long nvec,
+                     const double* __restrict__ sums3, int mode, float value, float max_norm, int inf_guard,
+                     float* __restrict__ param, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                     AdamScalars as, int zero_grads, float* __restrict__ grad_out, float* __restrict__ stats5) {
+    float s = 0.f, clip = 1.f;
+    if (sums3 != nullptr) {
+        const CombineScalars cs = combine_scalars_from(sums3[0], sums3[1], sums3[2], mode, value, max_norm, inf_guard,
+                                                       stats5, blockIdx.x == 0 && threadIdx.x == 0);
+        s = cs.s; clip = cs.clip;
+    }
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const long long chunk = (long long)kThreads * kOptUnroll;
+    const long long nchunks = (nvec + chunk - 1) / chunk;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const long long base = (nchunks - 1 - c) * chunk + threadIdx.x;   // reverse of K4a's walk (L2 tail reuse)
+        uint4 rx[kOptUnroll], ra[kOptUnroll], rp[kOptUnroll], rm[kOptUnroll], rv[kOptUnroll];
+        bool ok[kOptUnroll];
+#pragma unroll
+        for (int j = 0; j < kOptUnroll; ++j) {
+            const long long i = base + (long long)j * kThreads;
+            ok[j] = i < nvec;
+            if (ok[j]) {
+                rx[j] = ldg_v4(gx + 4 * i);
+                if (TWO_TERM) ra[j] = ldg_v4(ga + 4 * i);
+                rp[j] = ldg_v4(param + 4 * i);
+                rm[j] = ldg_v4(exp_avg + 4 * i);
+                rv[j] = ldg_v4(exp_avg_sq + 4 * i);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kOptUnroll; ++j) {
+            if (!ok[j]) continue;
+            const long long i = base + (long long)j * kThreads;
+            float x[4], a[4], p[4], m[4], v[4], g[4];
+            VecTraits<float>::unpack(rx[j], x);
+            if (TWO_TERM) VecTraits<float>::unpack(ra[j], a);
+            VecTraits<float>::unpack(rp[j], p);
+            VecTraits<float>::unpack(rm[j], m);
+            VecTraits<float>::unpack(rv[j], v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                g[q] = TWO_TERM ? __fmul_rn(__fsub_rn(x[q], __fmul_rn(s, a[q])), clip) : __fmul_rn(x[q], clip);
+                adam_update(g[q], p[q], m[q], v[q], as);
+            }
+            stg_stream(param + 4 * i, VecTraits<float>::pack(p));
+            stg_stream(exp_avg + 4 * i, VecTraits<float>::pack(m));
+            stg_stream(exp_avg_sq + 4 * i, VecTraits<float>::pack(v));
+            if (grad_out) stg_stream(grad_out + 4 * i, VecTraits<float>::pack(g));
+            if (zero_grads) {
+                if (grad_out != gx) stg_stream(gx + 4 * i, zero4);
+                if (TWO_TERM) stg_stream(ga + 4 * i, zero4);
+            }
+        }
+    }
+    {   // scalar remainder / unaligned buffers
+        const long long start = nvec * 4;
+        const long long stride = (long long)gridDim.x * kThreads;
+        for (long long i = start + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+            const float g = TWO_TERM ? __fmul_rn(__fsub_rn(gx[i], __fmul_rn(s, ga[i])), clip) : __fmul_rn(gx[i], clip);
+            float p = param[i], m = exp_avg[i], v = exp_avg_sq[i];
+            adam_update(g, p, m, v, as);
+            param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+            if (grad_out) grad_out[i] = g;
+            if (zero_grads) {
+                if (grad_out != gx) gx[i] = 0.f;
+                if (TWO_TERM) ga[i] = 0.f;
+            }
+        }
+    }
+}
+
+}  // namespace siss
+
+using namespace siss;
+
+extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const double* sums3, int mode, float value,
+                                  float max_norm, int inf_guard, float* param, float* exp_avg, float* exp_avg_sq,
+                                  double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                                  int zero_grads, float* grad_out, float* stats5, siss_stream_t stream) {
+    if (!g_x || !param || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return SISS_EINVAL;
+    if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_NONE) return SISS_EINVAL;
+    const bool two_term = (g_a != nullptr) && mode != SISS_COMBINE_NONE;
+    if (mode != SISS_COMBINE_NONE && (!g_a || !sums3)) return SISS_EINVAL;
+    // python-float scalars of torch.optim.AdamW's single-tensor path, rounded to fp32 where the tensor op does
+    AdamScalars as;
+    as.decay = (float)(1.0 - lr * weight_decay);
+    as.w1 = (float)(1.0 - beta1);
+    as.beta2 = (float)beta2;
+    as.w2 = (float)(1.0 - beta2);
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    as.bc2_sqrt = (float)sqrt(bc2);
+    as.neg_step = (float)(-(lr / bc1));
+    as.eps = (float)eps;
+    bool al = aligned16(g_x) && aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(grad_out);
+    if (two_term) al = al && aligned16(g_a);
+    const long long nvec = al ? n / 4 : 0;
+    const long long chunk = (long long)kThreads * kOptUnroll;
+    long long work = (nvec + chunk - 1) / chunk;
+    if (nvec * 4 < n) {
+        const long long tail_blocks = (n - nvec * 4 + kThreads - 1) / kThreads;
+        if (tail_blocks > work) work = tail_blocks;
+    }
+    long long grid = (long long)cached_sm_count() * kOptOcc;
+    if (work < grid) grid = work;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (two_term)
+        combine_adamw_kernel<true><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,
+                                                                   param, exp_avg, exp_avg_sq, as, zero_grads, grad_out, stats5);
+    else
+        combine_adamw_kernel<false><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,
+                                                                    param, exp_avg, exp_avg_sq, as, zero_grads, grad_out, stats5);
+    return (int)cudaGetLastError();
+}

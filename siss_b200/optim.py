@@ -1,0 +1,81 @@
+"""AdamW fused into the gradient combine.
+
+``FusedCombineAdamW`` is what ``GradCombiner.combine(...)`` followed by ``torch.optim.AdamW.step()`` and
+``optimizer.zero_grad()`` are in the reference loop (delete_celeb.py:714-773), as ONE pass over flat
+buffers: parameters, both moments and the two gradient buffers are each read once and written once
+(``siss_combine_adamw``), the combined gradient itself never goes to HBM.
+
+Parameters are moved into one flat fp32 buffer (``param.data`` become views, exactly like the gradients);
+the module keeps working unchanged. Under data parallel the exchange happens first (NCCL or the fused
+NVLink kernels of ``GradCombiner``), then every rank applies the identical update.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import SISS_COMBINE_ERASEDIFF, SISS_COMBINE_NONE, SISS_COMBINE_SCALING_NORM
+from .grad_combine import GradCombiner
+
+
+class FusedCombineAdamW:
+    def __init__(self, combiner: GradCombiner, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-2):
+        self.combiner = combiner
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), \
+            float(weight_decay)
+        dev = combiner.device
+        self.p_flat = torch.zeros(combiner.total, dtype=torch.float32, device=dev)
+        for p, off in zip(combiner.params, combiner.offsets):
+            view = self.p_flat[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+        self.exp_avg = torch.zeros_like(self.p_flat)
+        self.exp_avg_sq = torch.zeros_like(self.p_flat)
+        self.step_count = 0
+
+    def _launch(self, sums3: Optional[torch.Tensor], mode: int, value: float, max_norm: float, inf_guard: bool,
+                two_term: bool) -> None:
+        cb = self.combiner
+        self.step_count += 1
+        _lib.check(_lib.load().siss_combine_adamw(
+            ctypes.c_void_p(cb.g_x.data_ptr()), ctypes.c_void_p(cb.g_a.data_ptr() if two_term else 0), cb.total,
+            ctypes.c_void_p(0 if sums3 is None else sums3.data_ptr()), int(mode), float(value), float(max_norm),
+            int(bool(inf_guard)), ctypes.c_void_p(self.p_flat.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
+            ctypes.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
+            self.weight_decay, self.step_count, 1, ctypes.c_void_p(0), ctypes.c_void_p(cb.stats.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "siss_combine_adamw")
+        ops._count()
+
+    def step(self, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
+             max_norm: Optional[float] = 1.0, inf_guard: bool = False, single_term: bool = False) -> torch.Tensor:
+        """Sync-step combine + clip + AdamW + zero_grad. Give ``scaling_norm`` (SISS / No-IS), ``eta``
+        (EraseDiff) or ``single_term=True`` (naive_del / simple_neg_del). Returns the device stats tensor of
+        ``GradCombiner.combine``. Gradient buffers are left cleared."""
+        cb = self.combiner
+        mn = 0.0 if max_norm is None else float(max_norm)
+        if cb.world > 1:
+            # exchange + combine first (result in G_x on every rank), then the update on the combined gradient
+            if single_term:
+                cb.clip_only(mn)
+            else:
+                cb.combine(scaling_norm=scaling_norm, eta=eta, max_norm=max_norm, inf_guard=inf_guard)
+            self._launch(None, SISS_COMBINE_NONE, 0.0, 0.0, False, two_term=False)
+            cb._dirty_x = False          # G_x cleared by the kernel; G_a by combine()
+            cb._point(cb._views_x)
+            return cb.stats
+        if single_term:
+            ops.norm3(cb.g_x, cb.g_x, out=cb.sums3)
+            self._launch(cb.sums3, SISS_COMBINE_NONE, 0.0, mn, False, two_term=False)
+        else:
+            if (scaling_norm is None) == (eta is None):
+                raise ValueError("give exactly one of scaling_norm= or eta= (or single_term=True)")
+            mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF
+            ops.norm3(cb.g_x, cb.g_a, out=cb.sums3)
+            self._launch(cb.sums3, mode, float(scaling_norm if eta is None else eta), mn, inf_guard, two_term=True)
+        cb._dirty_x = False
+        cb._point(cb._views_x)
+        return cb.stats

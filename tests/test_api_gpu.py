@@ -277,3 +277,47 @@ def test_fused_batch_stats_match_reference_stats_block(name, dev):
     recs = log.pop_ready(wait=True)
     assert [r["step"] for r in recs] == [1, 2] and recs[-1]["gradient/scaling_factor"] == 2.0
     assert recs[-1]["loss_x/mean"] == pytest.approx(ref["loss_x/mean"], rel=2e-5)
+
+
+@pytest.mark.parametrize("loss_fn,kw", [("importance_sampling_with_mixture", dict(lambd=0.5, scaling_norm=5.0)),
+                                        ("naive_del", dict())])
+def test_fused_combine_adamw_matches_reference_loop_plus_torch_adamw(loss_fn, kw, dev):
+    """§8(f)2: three optimiser steps of [reference loop + clip + torch.optim.AdamW + zero_grad] on CPU vs
+    [UnlearnStep.micro_step + FusedCombineAdamW.step] on the GPU. lr is large so the update is well above
+    fp32 noise in the parameters."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.optim import FusedCombineAdamW
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    B, G = 4, 2
+    hp = dict(lr=3e-3, betas=(0.95, 0.999), eps=1e-8, weight_decay=1e-2)
+    cpu_net = TinyNet(); gpu_net = copy.deepcopy(cpu_net).to(dev)
+    sched = SissDDPMScheduler()
+    oloss = O.OracleDeletionLoss(*O.gamma_sigma(sched.alphas_cumprod))
+    loop = O.ReferenceGradLoop(cpu_net, train_batch_size=B, grad_accum_steps=G)
+    ref_opt = torch.optim.AdamW(cpu_net.parameters(), **hp)
+    comb = GradCombiner(gpu_net.parameters())
+    opt = FusedCombineAdamW(comb, **hp)
+    step = UnlearnStep(gpu_net, sched, comb, loss_fn=loss_fn, train_batch_size=B, gradient_accumulation_steps=G,
+                       max_norm=1.0, **kw)
+    single = loss_fn == "naive_del"
+    torch.manual_seed(31)
+    for it in range(3):
+        for k in range(G):
+            x0, a0 = torch.rand(B, 1, 8, 8) * 2 - 1, torch.rand(B, 1, 8, 8) * 2 - 1
+            noise, t = torch.randn(B, 1, 8, 8), torch.randint(300, 1000, (B,))
+            keep = torch.rand(B) > 0.5
+            all_d = {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)}
+            del_d = {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}
+            okw = dict(lambd=0.5, keep_mask=keep) if not single else {}
+            loop.micro_step(getattr(oloss, loss_fn)(cpu_net, t, noise, {}, all_d, del_d, **okw), retain_graph=not single)
+            step.micro_step(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev), keep_mask=keep)
+        loop.sync_step(single, loss_fn, scaling_norm=kw.get("scaling_norm"), max_norm=1.0)
+        ref_opt.step(); ref_opt.zero_grad()
+        step._micro = 0
+        opt.step(scaling_norm=kw.get("scaling_norm"), max_norm=1.0, single_term=single)
+        assert comb.g_x.abs().max().item() == 0.0 and comb.g_a.abs().max().item() == 0.0   # zero_grad folded in
+        for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
+            assert p.data_ptr() >= opt.p_flat.data_ptr()                                    # params live in the flat buffer
+            torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=3e-5, atol=3e-6)
