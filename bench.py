@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--dtype", choices=["bf16", "fp32", "fp16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=16)
     ap.add_argument("--transport", choices=["auto", "p2p", "nccl"], default="auto",
                     help="N>1 gradient exchange: fused NVLink peer-memory kernels or NCCL collectives")
     return ap.parse_args()
@@ -306,7 +306,7 @@ def run_siss(args):
     Ptot = (P + pad - 1) // pad * pad
     peer = None
     transport = "single" if n == 1 else "nccl"
-    if n > 1 and args.transport in ("auto", "p2p"):
+    if n > 1 and (args.transport == "p2p" or (args.transport == "auto" and n in (2, 4))):
         try:
             from siss_b200.p2p import PeerExchange
             peer = PeerExchange(Ptot, dev)

@@ -225,10 +225,16 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
                     if (Op::ub(i) == 32) in[i][1] = lds128(base + 16);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);   // this warp is done reading the stage
-            if (++stage == S) { stage = 0; phase ^= 1u; }
             if (ok) Op::unit(p, r, in, row * s.upr + u, acc);
+            // Release the stage only AFTER the unit's math and global stores: those truly depend on the
+            // registers the LDS above fill, so the shared-memory reads have completed by now. Releasing
+            // right after *issuing* the LDS raced with the producer's next bulk copy (async proxy) under
+            // MIO back-pressure: ~80 corrupted units per 1.5 M in K3 at the celeb shape, caught by
+            // tests/test_fullsize_gpu.py. The ring is 5-6 stages deep, so holding a stage for one unit's
+            // compute costs nothing measurable.
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         if constexpr (Op::K > 0) {
             double tot[Op::K];
