@@ -70,9 +70,10 @@ int siss_add_noise_pair(const void* x0, const void* a0, const void* noise, const
                         int64_t B, int64_t D, int dtype, siss_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Workspace for the per-sample (row) reductions of K2 / K3. Allocate once, ZERO it once
- * (cudaMemset) and reuse: the kernels leave their ticket counters reset. Size depends only on
- * the largest B it will be used with.
+ * Workspace for the per-sample (row) reductions and the dynamic span queue of K2 / K3. Allocate
+ * once, ZERO it once (cudaMemset) and reuse on one stream: the kernels leave every counter reset,
+ * and the layout does not depend on the per-call B, so calls with different batch sizes can share
+ * it. Size depends only on the largest B it will be used with (~150 KB + 4 B per row).
  * ---------------------------------------------------------------------------------------- */
 int64_t siss_row_workspace_bytes(int64_t B);
 

@@ -83,7 +83,8 @@ __device__ __forceinline__ void consumer_block_sum(float (&v)[K], float* smem) {
 // row_reduce for the consumer threads of a pipelined kernel (see rowtile.cuh::row_reduce).
 template <int K>
 __device__ __forceinline__ bool consumer_row_reduce(float (&acc)[K], double (&tot)[K], const RowSched& s,
-                                                    const RowWorkspace& ws, long long row, float* red, int* flag) {
+                                                    const RowWorkspace& ws, long long row, bool row_began_before_span,
+                                                    float* red, int* flag) {
     static_assert(K <= 3, "slot holds 3 values");
     consumer_block_sum<K>(acc, red);
     const long long rs = row * s.upr;
@@ -94,10 +95,10 @@ __device__ __forceinline__ bool consumer_row_reduce(float (&acc)[K], double (&to
         return threadIdx.x < 32;
     }
     if (threadIdx.x == 0) {
-        st_slot(ws.partials + ((long long)blockIdx.x + row) * kRowPartialStride, acc[0], K > 1 ? acc[1] : 0.f,
-                K > 2 ? acc[2] : 0.f);
+        st_slot(ws.partials + partial_slot(blockIdx.x, row_began_before_span) * kRowPartialStride, acc[0],
+                K > 1 ? acc[1] : 0.f, K > 2 ? acc[2] : 0.f);
         __threadfence();
-        unsigned int* counter = ws.counters + row;
+        unsigned int* counter = ws.counters + 1 + row;
         const unsigned int tk = atomicAdd(counter, 1u);
         const int is_last = (tk == (unsigned)(last - first));
         if (is_last) *counter = 0u;
@@ -107,10 +108,9 @@ __device__ __forceinline__ bool consumer_row_reduce(float (&acc)[K], double (&to
     if (*flag == 0 || threadIdx.x >= 32) return false;
     __threadfence();
     double t[3] = {0.0, 0.0, 0.0};
-    const float* base = ws.partials + ((long long)first + row) * kRowPartialStride;
     const int n = last - first + 1;
-    for (int i = threadIdx.x; i < n; i += 32) {
-        const float4 v = ld_slot(base + (long long)i * kRowPartialStride);
+    for (int i = threadIdx.x; i < n; i += 32) {   // contributors are the consecutive spans first..last
+        const float4 v = ld_slot(ws.partials + partial_slot(first + i, i != 0) * kRowPartialStride);
         t[0] += (double)v.x; t[1] += (double)v.y; t[2] += (double)v.z;
     }
 #pragma unroll
@@ -238,7 +238,7 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
         }
         if constexpr (Op::K > 0) {
             double tot[Op::K];
-            if (consumer_row_reduce<Op::K>(acc, tot, s, ws, row, red, &flag) && threadIdx.x == 0)
+            if (consumer_row_reduce<Op::K>(acc, tot, s, ws, row, seg.begin > 0, red, &flag) && threadIdx.x == 0)
                 Op::row_end(p, r, row, tot);
         }
     }

@@ -21,7 +21,8 @@
 
 namespace siss {
 
-constexpr int kMaxGrid = 148 * 8;         // upper bound on any row-kernel grid (slots workspace)
+constexpr int kMaxGrid = 148 * 8;         // upper bound on any row-kernel grid
+constexpr int kMaxSpans = kMaxGrid * 4;   // upper bound on the number of spans (slots workspace)
 constexpr int kRowPartialStride = 4;      // floats per partial slot (one 128-bit access)
 
 struct RowSched {
@@ -30,11 +31,20 @@ struct RowSched {
     long long upr;   // units per row = ceil(D / W)
     long long U;     // total units = B * upr
     int grid;        // CTAs to launch
+    int nspans;      // contiguous spans the unit space is cut into. Currently == grid (span id == blockIdx.x).
+                     // A dynamic span queue (several spans per CTA, claimed with atomicAdd) was built and
+                     // measured in round 1: at the celeb shape a CTA has only ~14 stages of work, so the
+                     // per-span claim + row-setup cost exceeded what balancing recovered (K1oK2 32.6-47 us
+                     // vs 31.6 us static); kept out, see DESIGN.md.
 };
 
 int cached_sm_count();
 
-inline RowSched make_row_sched(long long B, long long D, int W, int ctas_per_sm) {
+// tuning knobs for the dynamically scheduled kernels (read once; see tools/ for the sweep that set the defaults)
+int env_int(const char* name, int dflt);
+
+inline RowSched make_row_sched(long long B, long long D, int W, int ctas_per_sm, int spans_per_cta = 1,
+                               int min_span_stages = 8) {
     RowSched s;
     s.B = B; s.D = D;
     s.upr = (D + W - 1) / W;
@@ -45,19 +55,34 @@ inline RowSched make_row_sched(long long B, long long D, int W, int ctas_per_sm)
     long long want = (s.U + kThreads - 1) / kThreads;
     s.grid = (int)(want < slots ? want : slots);
     if (s.grid < 1) s.grid = 1;
+    // dynamic scheduling: up to spans_per_cta spans per CTA, but never spans shorter than 8 stages
+    long long ns = s.grid;
+    if (spans_per_cta > 1) {
+        const long long by_size = s.U / ((long long)min_span_stages * kThreads);
+        ns = (long long)s.grid * spans_per_cta;
+        if (ns > by_size) ns = by_size;
+        if (ns < s.grid) ns = s.grid;
+        if (ns > kMaxSpans) ns = kMaxSpans;
+    }
+    s.nspans = (int)ns;
     return s;
 }
 
-// span of CTA c: [floor(c U / G), floor((c+1) U / G))
-__device__ __forceinline__ void cta_span(const RowSched& s, long long& u0, long long& u1) {
-    const long long g = gridDim.x, c = blockIdx.x;
+// span c: [floor(c U / S), floor((c+1) U / S)),  S = nspans
+__device__ __forceinline__ void span_range(const RowSched& s, long long c, long long& u0, long long& u1) {
+    const long long g = s.nspans;
     u0 = (c * s.U) / g;
     u1 = ((c + 1) * s.U) / g;
 }
 
-// the CTA whose span contains unit u (inverse of the floor partition above)
+// statically scheduled kernels: span id == blockIdx.x (nspans == gridDim.x)
+__device__ __forceinline__ void cta_span(const RowSched& s, long long& u0, long long& u1) {
+    span_range(s, blockIdx.x, u0, u1);
+}
+
+// the span that contains unit u (inverse of the floor partition above)
 __device__ __forceinline__ int span_owner(const RowSched& s, long long u) {
-    return (int)(((u + 1) * (long long)gridDim.x - 1) / s.U);
+    return (int)(((u + 1) * (long long)s.nspans - 1) / s.U);
 }
 
 // torch-style index: negative wraps once, then clamp for memory safety (eager would raise).
@@ -68,26 +93,35 @@ __device__ __forceinline__ int wrap_timestep(long long t, int T) {
     return (int)t;
 }
 
-// Workspace: [B] ticket counters (zero between launches; the kernels restore that) followed by
-// (kMaxGrid + B) partial slots of kRowPartialStride floats.
+// Workspace layout — every position is INDEPENDENT of the per-call B, so one zero-initialised
+// workspace can be reused across calls with different batch sizes (the kernels leave it clean):
+//   [0, kSlotBytes)            partial slots, 2 per span: a span has at most two row segments that
+//                              share their row with another span (its first and its last), all rows
+//                              in between are complete inside the span and need no slot.
+//                                slot(span c, segment) = 2c      if the row began before the span
+//                                                        2c + 1  if the row begins inside it
+//   [kSlotBytes, +4)           span-claim counter (dynamic scheduling)
+//   [kSlotBytes + 4*(1+r))     ticket counter of row r
 struct RowWorkspace {
-    unsigned int* counters;
+    unsigned int* counters;   // [0] span-claim counter, [1 + r] ticket of row r
     float* partials;
 };
 
-inline long long row_ws_counter_bytes(long long B) {
-    return ((B * (long long)sizeof(unsigned int) + 255) / 256) * 256;
-}
+constexpr long long kSlotBytes = 2LL * kMaxSpans * kRowPartialStride * (long long)sizeof(float);
 
 inline long long row_ws_bytes(long long B) {
-    return row_ws_counter_bytes(B) + (B + kMaxGrid) * (long long)kRowPartialStride * (long long)sizeof(float);
+    return kSlotBytes + (((B + 1) * (long long)sizeof(unsigned int) + 255) / 256) * 256;
 }
 
-inline RowWorkspace carve_row_workspace(void* ws, long long B) {
+inline RowWorkspace carve_row_workspace(void* ws, long long /*B*/) {
     RowWorkspace r;
-    r.counters = reinterpret_cast<unsigned int*>(ws);
-    r.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + row_ws_counter_bytes(B));
+    r.partials = reinterpret_cast<float*>(ws);
+    r.counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kSlotBytes);
     return r;
+}
+
+__device__ __forceinline__ long long partial_slot(long long span, bool row_began_before_span) {
+    return 2 * span + (row_began_before_span ? 0 : 1);
 }
 
 // 128-bit L2-coherent load/store of a partial slot (other SMs wrote it: bypass L1)
@@ -107,7 +141,7 @@ __device__ __forceinline__ void st_slot(float* p, float a, float b, float c) {
 // Call from ALL threads (contains __syncthreads).
 template <int K>
 __device__ __forceinline__ bool row_reduce(float (&acc)[K], double (&tot)[K], const RowSched& s, const RowWorkspace& ws,
-                                           long long row, float* red, int* flag) {
+                                           long long row, bool row_began_before_span, float* red, int* flag) {
     static_assert(K <= 3, "slot holds 3 values");
     block_sum<K>(acc, red);
     const long long rs = row * s.upr;
@@ -119,10 +153,10 @@ __device__ __forceinline__ bool row_reduce(float (&acc)[K], double (&tot)[K], co
     }
     // Only thread 0 publishes, so only thread 0 needs the (expensive, store-draining) device fence.
     if (threadIdx.x == 0) {
-        st_slot(ws.partials + ((long long)blockIdx.x + row) * kRowPartialStride, acc[0], K > 1 ? acc[1] : 0.f,
-                K > 2 ? acc[2] : 0.f);
+        st_slot(ws.partials + partial_slot(blockIdx.x, row_began_before_span) * kRowPartialStride, acc[0],
+                K > 1 ? acc[1] : 0.f, K > 2 ? acc[2] : 0.f);
         __threadfence();
-        unsigned int* counter = ws.counters + row;
+        unsigned int* counter = ws.counters + 1 + row;
         const unsigned int tk = atomicAdd(counter, 1u);
         const int is_last = (tk == (unsigned)(last - first));
         if (is_last) *counter = 0u;  // leave the workspace clean for the next launch
@@ -132,10 +166,9 @@ __device__ __forceinline__ bool row_reduce(float (&acc)[K], double (&tot)[K], co
     if (*flag == 0 || threadIdx.x >= 32) return false;
     __threadfence();  // acquire side
     double t[3] = {0.0, 0.0, 0.0};
-    const float* base = ws.partials + ((long long)first + row) * kRowPartialStride;
     const int n = last - first + 1;
-    for (int i = threadIdx.x; i < n; i += 32) {
-        const float4 v = ld_slot(base + (long long)i * kRowPartialStride);
+    for (int i = threadIdx.x; i < n; i += 32) {   // contributors are the consecutive spans first..last
+        const float4 v = ld_slot(ws.partials + partial_slot(first + i, i != 0) * kRowPartialStride);
         t[0] += (double)v.x; t[1] += (double)v.y; t[2] += (double)v.z;
     }
 #pragma unroll

@@ -23,6 +23,13 @@ int cached_sm_count() {
     return sms;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = std::atoi(e);
+    return v > 0 ? v : dflt;
+}
+
 // A/B switch for measurements: SISS_NO_TMA=1 forces the plain-LDG kernels on the vector path too.
 bool use_tma_pipeline() {
     static int v = -1;
@@ -252,7 +259,7 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
         }
 
         double tot[3];
-        if (row_reduce<3>(acc, tot, s, ws, row, red, &flag) && threadIdx.x == 0)
+        if (row_reduce<3>(acc, tot, s, ws, row, sg.begin > 0, red, &flag) && threadIdx.x == 0)
             finalize_row_weights(tot[0], tot[1], tot[2], sigma[t], lam, one_m_lam, row, dist_x, dist_a, w_x, w_a);
     }
 }

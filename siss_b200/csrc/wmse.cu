@@ -130,7 +130,7 @@ wmse_fwd_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, co
             }
         }
         double tot[2];
-        if (row_reduce<2>(acc, tot, rt, ws, row, red, &flag) && threadIdx.x == 0) {
+        if (row_reduce<2>(acc, tot, rt, ws, row, seg.begin > 0, red, &flag) && threadIdx.x == 0) {
             row_loss_x[row] = (float)tot[0];
             row_loss_a[row] = (float)tot[1];
         }
@@ -427,7 +427,7 @@ dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
             }
         }
         double tot[2];
-        if (row_reduce<2>(acc, tot, rt, ws, row, red, &flag) && threadIdx.x == 0) {
+        if (row_reduce<2>(acc, tot, rt, ws, row, seg.begin > 0, red, &flag) && threadIdx.x == 0) {
             row_loss_x[row] = (float)tot[0];
             row_loss_a[row] = (float)tot[1];
         }

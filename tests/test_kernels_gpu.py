@@ -330,3 +330,31 @@ def test_combine_inplace_misaligned_and_guards(dev):
     # no clip requested
     o, st = ops.combine(x * 1e3, z, ops.norm3(x * 1e3, z), _lib.SISS_COMBINE_NONE, 0.0, 0.0)
     assert st[4].item() == 1.0 and torch.equal(o, x * 1e3)
+
+
+def test_workspace_reuse_across_batch_sizes(dev):
+    """One zero-initialised row workspace serves calls with different B and D in any order (its layout
+    does not depend on the per-call B). Regression test: partial sums of a small-B call used to land
+    where a later large-B call kept its ticket / span-claim counters."""
+    from siss_b200 import ops
+    ac = O.make_alphas_cumprod(); gamma, sigma = O.gamma_sigma(ac)
+    order = [(4, 3, 256, 256), (64, 1, 28, 28), (300, 4, 8, 8), (2, 3, 256, 256), (130, 1, 28, 28), (4, 3, 256, 256),
+             (64, 1, 28, 28)]
+    for i, shape in enumerate(order):
+        torch.manual_seed(100 + i)
+        B = shape[0]
+        x0 = torch.rand(shape) * 2 - 1; a0 = torch.rand(shape) * 2 - 1; n = torch.randn(shape)
+        t = torch.randint(0, 1000, (B,)); keep = torch.rand(B) > 0.5
+        mix = O.select_mixture(O.add_noise(ac, x0, n, t), O.add_noise(ac, a0, n, t), keep)
+        ed_x, ed_a = O.gaussian_exponents(mix, x0, a0, gamma[t], sigma[t])
+        out = ops.add_noise_mixture(x0.to(dev), a0.to(dev), n.to(dev), keep, t.to(dev), ac, gamma, sigma, 0.5)
+        _bits_equal(out[0], mix, f"x_mix {shape}")
+        torch.testing.assert_close(out[1].cpu(), ed_x, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(out[2].cpu(), ed_a, rtol=1e-5, atol=1e-6)
+        pred = torch.randn(shape)
+        gx, ga, rlx, rla = ops.wmse_fwd_bwd(pred.to(dev), out[0], x0.to(dev), a0.to(dev), t.to(dev), gamma, sigma,
+                                            out[3], out[4], 1 / 64, 1 / 64)
+        eps_x = (mix - gamma[t].view(-1, 1, 1, 1) * x0) / sigma[t].view(-1, 1, 1, 1)
+        torch.testing.assert_close(rlx.cpu(), ((pred - eps_x) ** 2).sum(dim=[1, 2, 3]), rtol=1e-5, atol=1e-5)
+    ws = list(ops._row_ws.values())
+    assert len(ws) >= 1
