@@ -209,6 +209,27 @@ int siss_combine(const float* g_x, const float* g_a, float* out, int64_t n,
                  float* stats5, siss_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-tensor K4 — K4a / K4b over a LIST of separately allocated gradient tensors (one per UNet
+ * parameter, the layout of the reference loop, delete_celeb.py:717-750), for callers that keep
+ * per-parameter tensors instead of GradCombiner's flat buffers. One launch for the whole list.
+ * All `d_*` arrays live in DEVICE memory and are built once by the caller:
+ *   d_gx[i], d_ga[i], d_out[i]  pointers of tensor i (d_out[i] may equal d_gx[i]);
+ *   d_sizes[i]                  elements of tensor i;
+ *   d_chunk_prefix[i]           number of siss_mt_chunk_elems()-element chunks in tensors 0..i-1,
+ *                               d_chunk_prefix[n_tensors] == total_chunks.
+ * Same arithmetic, scalars and stats as siss_norm3 / siss_combine; workspace as siss_norm3.
+ * ---------------------------------------------------------------------------------------- */
+int siss_mt_chunk_elems(void);
+
+int siss_mt_norm3(const float* const* d_gx, const float* const* d_ga, const int64_t* d_sizes,
+                  const int64_t* d_chunk_prefix, int n_tensors, int64_t total_chunks, double* sums3,
+                  void* workspace, siss_stream_t stream);
+
+int siss_mt_combine(const float* const* d_gx, const float* const* d_ga, float* const* d_out, const int64_t* d_sizes,
+                    const int64_t* d_chunk_prefix, int n_tensors, int64_t total_chunks, const double* sums3,
+                    int mode, float value, float max_norm, int inf_guard, float* stats5, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K4b fused with the optimiser step: g = clip * (g_x - s * g_a) is consumed in registers by a
  * torch.optim.AdamW update (decoupled weight decay; config/delete_celeb.yaml:127-134, stepped at
  * delete_celeb.py:769) of the flat fp32 parameter buffer `param` and its moments; with zero_grads the

@@ -415,3 +415,57 @@ def batch_stats(row_loss_x: Optional[torch.Tensor], row_loss_a: Optional[torch.T
                                             int(elems_per_sample), _ptr(out), _stream()), "siss_batch_stats")
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-tensor K4 (per-parameter gradient tensors, no flat buffers)
+# ------------------------------------------------------------------------------------------------
+class MultiTensorPlan:
+    """Device-side pointer/size/chunk tables for ``siss_mt_norm3`` / ``siss_mt_combine`` over lists of fp32
+    tensors ``accum_x[i]``, ``accum_a[i]`` (and ``out[i]``, default: write back into ``accum_x[i]``). Build
+    once per set of tensors; the tables hold raw pointers, so the tensors must stay alive and in place."""
+
+    def __init__(self, accum_x, accum_a, out=None):
+        accum_x, accum_a = list(accum_x), list(accum_a)
+        out = accum_x if out is None else list(out)
+        if not accum_x or not (len(accum_x) == len(accum_a) == len(out)):
+            raise ValueError("need equally long, non-empty tensor lists")
+        self.dev = _need_cuda(*accum_x, *accum_a, *out)
+        for x, a, o in zip(accum_x, accum_a, out):
+            if not (x.dtype == a.dtype == o.dtype == torch.float32):
+                raise SissLibraryError("multi-tensor combine handles float32 gradients")
+            if not (x.numel() == a.numel() == o.numel()) or not (x.is_contiguous() and a.is_contiguous() and o.is_contiguous()):
+                raise ValueError("tensors of one index must be contiguous and equally sized")
+        self.keep = (accum_x, accum_a, out)
+        chunk = _lib.load().siss_mt_chunk_elems()
+        sizes = [x.numel() for x in accum_x]
+        prefix = [0]
+        for n in sizes:
+            prefix.append(prefix[-1] + (n + chunk - 1) // chunk)
+        i64 = dict(dtype=torch.int64, device=self.dev)
+        self.n = len(sizes)
+        self.total_chunks = prefix[-1]
+        self.gx = torch.tensor([t.data_ptr() for t in accum_x], **i64)
+        self.ga = torch.tensor([t.data_ptr() for t in accum_a], **i64)
+        self.out = torch.tensor([t.data_ptr() for t in out], **i64)
+        self.sizes = torch.tensor(sizes, **i64)
+        self.prefix = torch.tensor(prefix, **i64)
+        self.sums3 = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self.stats = torch.zeros(5, dtype=torch.float32, device=self.dev)
+
+    def norm3(self) -> torch.Tensor:
+        _lib.check(_lib.load().siss_mt_norm3(_ptr(self.gx), _ptr(self.ga), _ptr(self.sizes), _ptr(self.prefix), self.n,
+                                             self.total_chunks, _ptr(self.sums3), _ptr(_norm_workspace(self.dev)),
+                                             _stream()), "siss_mt_norm3")
+        _count()
+        return self.sums3
+
+    def combine(self, mode: int, value: float, max_norm: float = 1.0, inf_guard: bool = False) -> torch.Tensor:
+        """K4a + K4b over the list; results land in ``out[i]``. Returns the device stats5 tensor."""
+        self.norm3()
+        _lib.check(_lib.load().siss_mt_combine(_ptr(self.gx), _ptr(self.ga), _ptr(self.out), _ptr(self.sizes),
+                                               _ptr(self.prefix), self.n, self.total_chunks, _ptr(self.sums3), int(mode),
+                                               float(value), float(max_norm if max_norm is not None else 0.0),
+                                               int(bool(inf_guard)), _ptr(self.stats), _stream()), "siss_mt_combine")
+        _count()
+        return self.stats

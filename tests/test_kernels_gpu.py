@@ -358,3 +358,39 @@ def test_workspace_reuse_across_batch_sizes(dev):
         torch.testing.assert_close(rlx.cpu(), ((pred - eps_x) ** 2).sum(dim=[1, 2, 3]), rtol=1e-5, atol=1e-5)
     ws = list(ops._row_ws.values())
     assert len(ws) >= 1
+
+
+@pytest.mark.parametrize("mode", ["scaling_norm", "erasediff"])
+def test_multi_tensor_combine_matches_reference_dict_loop(mode, dev):
+    """siss_mt_norm3 / siss_mt_combine over a ragged list of per-parameter tensors (sizes 1 .. 70k, one of
+    them a 4-byte-offset view so its chunks take the scalar path) vs the oracle's flat evaluation of the
+    reference's dict loop (delete_celeb.py:717-767), and vs the flat-buffer kernels."""
+    from siss_b200 import ops, _lib
+    torch.manual_seed(4)
+    sizes = [1, 3, 4096, 4097, 70001, 513, 8192, 7]
+    xs = [torch.randn(n) * 3e-2 for n in sizes]
+    as_ = [torch.randn(n) * 1e-2 + 2e-3 for n in sizes]
+    dx = [t.to(dev) for t in xs]; da = [t.to(dev) for t in as_]
+    base = torch.zeros(sizes[5] + 1, device=dev); base[1:] = dx[5]; dx[5] = base[1:]      # misaligned tensor
+    assert dx[5].data_ptr() % 16 != 0
+    outs = [torch.empty_like(t) for t in dx]
+    plan = ops.MultiTensorPlan(dx, da, outs)
+    kw = dict(scaling_norm=5.0) if mode == "scaling_norm" else dict(eta=0.05)
+    m = _lib.SISS_COMBINE_SCALING_NORM if mode == "scaling_norm" else _lib.SISS_COMBINE_ERASEDIFF
+    stats = plan.combine(m, 5.0 if mode == "scaling_norm" else 0.05, 1.0).cpu().double()
+    fx, fa = torch.cat(xs), torch.cat(as_)
+    ref = torch.tensor([(fx.double() ** 2).sum(), (fa.double() ** 2).sum(), (fx.double() * fa.double()).sum()])
+    torch.testing.assert_close(plan.sums3.cpu(), ref, rtol=1e-12, atol=1e-300)
+    exp, nx, na, s, tn, clip = O.combine_flat(fx.double(), fa.double(), max_norm=1.0, **kw)
+    got = torch.cat([o.cpu() for o in outs]).double()
+    scale = float(exp.abs().max())
+    torch.testing.assert_close(got, exp, rtol=2e-6, atol=max(2e-6 * scale, 4e-7 * float((fx.abs() + (s * fa).abs()).max())))
+    torch.testing.assert_close(stats, torch.stack([nx, na, s.double(), tn, clip.double()]), rtol=2e-6, atol=2e-7)
+    # identical to the flat-buffer kernels on the concatenated tensors (same arithmetic, other reduction order)
+    flat_out, flat_stats = ops.combine(fx.to(dev), fa.to(dev), ops.norm3(fx.to(dev), fa.to(dev)), m,
+                                       5.0 if mode == "scaling_norm" else 0.05, 1.0)
+    torch.testing.assert_close(got.float(), flat_out.cpu(), rtol=1e-6, atol=1e-9)
+    # in-place form: out defaults to accum_x
+    plan2 = ops.MultiTensorPlan(dx, da)
+    plan2.combine(m, 5.0 if mode == "scaling_norm" else 0.05, 1.0)
+    torch.testing.assert_close(torch.cat([t.cpu() for t in dx]).double(), got, rtol=0, atol=0)
