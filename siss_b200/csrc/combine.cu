@@ -65,13 +65,17 @@ norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long lo
             float x[4], a[4];
             VecTraits<float>::unpack(rx[j], x);
             VecTraits<float>::unpack(ra[j], a);
+            // per-float4 partial sums first: the dependent DFMA chain on each accumulator is one DADD per
+            // float4 instead of four DFMAs (the 16 elements of an iteration are otherwise one serial chain)
+            double pxx = 0.0, paa = 0.0, pxa = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double xd = (double)x[q], ad = (double)a[q];
-                acc[0] = fma(xd, xd, acc[0]);
-                acc[1] = fma(ad, ad, acc[1]);
-                acc[2] = fma(xd, ad, acc[2]);
+                pxx = fma(xd, xd, pxx);
+                paa = fma(ad, ad, paa);
+                pxa = fma(xd, ad, pxa);
             }
+            acc[0] += pxx; acc[1] += paa; acc[2] += pxa;
         }
     }
     // scalar remainder (n % 4 elements, or everything when the buffers are not 16B aligned)

@@ -14,8 +14,15 @@ bool use_tma_pipeline();
 
 // u_x = pred - (x_mix - gamma*x0)/sigma  — losses/ddpm_deletion_loss.py:26,29 in eager's order:
 // mul, sub, div, sub, each rounded to fp32.
-__device__ __forceinline__ float residual(float pred, float xm, float g, float sg, float x) {
-    return __fsub_rn(pred, __fdiv_rn(__fsub_rn(xm, __fmul_rn(g, x)), sg));
+// The division: sigma is constant per row, so the quotient is formed as (float)((double)r * inv_sg)
+// with inv_sg = 1.0 / (double)sigma computed once per row. That IS the correctly rounded fp32 quotient:
+// the product carries two fp64 roundings (relative error < 2^-52), while a quotient of two 24-bit
+// significands is never closer than ~2^-49 (relative) to an fp32 rounding boundary (the classic
+// "2p+2 bits suffice" argument for division), so the final rounding decides exactly as IEEE division
+// does. 2 cvt + 1 DMUL instead of the ~9-instruction div.rn routine; K3 is issue-heavy, this matters.
+__device__ __forceinline__ float residual(float pred, float xm, float g, double inv_sg, float x) {
+    const float r = __fsub_rn(xm, __fmul_rn(g, x));
+    return __fsub_rn(pred, (float)((double)r * inv_sg));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -86,7 +93,8 @@ wmse_fwd_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, co
         const RowSeg seg = row_segment(rt, u0, u1, row);
         const long long rowoff = row * rt.D;
         const int t = wrap_timestep(ts[row], T_steps);
-        const float g = gamma[t], sg = sigma[t];
+        const float g = gamma[t];
+        const double sg = 1.0 / (double)sigma[t];   // reciprocal in fp64, see residual()
         // autograd: grad(weighted_loss) = go ; grad(loss) = go * w  (mul backward, rounded once)
         const float cx = __fmul_rn(go_x, w_x[row]);
         const float ca = __fmul_rn(go_a, w_a[row]);
@@ -158,7 +166,8 @@ wmse_fwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, const 
         const RowSeg seg = row_segment(rt, u0, u1, row);
         const long long rowoff = row * rt.D;
         const int t = wrap_timestep(ts[row], T_steps);
-        const float g = gamma[t], sg = sigma[t];
+        const float g = gamma[t];
+        const double sg = 1.0 / (double)sigma[t];   // reciprocal in fp64, see residual()
         const float wx = w_x[row], wa = w_a[row];
         for (long long ub = seg.begin; ub < seg.end; ub += (long long)kThreads * VPT) {
             typename PIO::Raw rp[VPT];
@@ -242,7 +251,8 @@ wmse_bwd_kernel(const TP* __restrict__ pred, const T* __restrict__ x_mix, const 
         const RowSeg seg = row_segment(rt, u0, u1, row);
         const long long rowoff = row * rt.D;
         const int t = wrap_timestep(ts[row], T_steps);
-        const float g = gamma[t], sg = sigma[t];
+        const float g = gamma[t];
+        const double sg = 1.0 / (double)sigma[t];   // reciprocal in fp64, see residual()
         const float wx = w_x[row], wa = w_a[row];
         for (long long ub = seg.begin; ub < seg.end; ub += (long long)kThreads * VPT) {
             const long long u = ub + threadIdx.x;
@@ -483,11 +493,11 @@ struct WmseFwdBwdOp {
         const float* gamma; const float* sigma; int T_steps; const float* w_x; const float* w_a;
         float go_x, go_a; TP* grad_x; TP* grad_a; float* row_loss_x; float* row_loss_a;
     };
-    struct Row { float g, sg, cx, ca; };
+    struct Row { float g, cx, ca; double sg; };   // sg = 1 / sigma_t in fp64, see residual()
     __device__ static __forceinline__ Row row_begin(const Params& p, long long row) {
         Row r;
         const int t = wrap_timestep(p.ts[row], p.T_steps);
-        r.g = p.gamma[t]; r.sg = p.sigma[t];
+        r.g = p.gamma[t]; r.sg = 1.0 / (double)p.sigma[t];
         r.cx = __fmul_rn(p.go_x, p.w_x[row]);   // mul backward: grad * w, rounded once
         r.ca = __fmul_rn(p.go_a, p.w_a[row]);
         return r;
