@@ -604,7 +604,11 @@ static int launch_wmse_fwd_bwd(const void* pred, const void* x_mix, const void* 
                                void* workspace, long long B, long long D, cudaStream_t st) {
     constexpr int W = VecTraits<T>::N;
     RowWorkspace ws = carve_row_workspace(workspace, B);
-    if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a) && use_tma_pipeline()) {
+    // Measured on B200 (profiles/r1_microbench_sweep.csv, celeb shape, bf16 latents): the TMA-fed kernel wins
+    // while the launch is short (B = 64: 50.7 vs 54.3 us), the register-staged LDG kernel wins once there
+    // are many iterations per CTA (B = 256: 166 vs 173 us, B = 1024: 605 vs 654 us). Switch at 4 M units.
+    const bool prefer_tma = (B * (D / W)) < (4LL << 20);
+    if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a) && use_tma_pipeline() && prefer_tma) {
         using Op = WmseFwdBwdOp<TP, T>;
         typename Op::Params p{(const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps,
                               w_x, w_a, go_x, go_a, (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a};
