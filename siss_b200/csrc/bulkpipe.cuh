@@ -163,7 +163,7 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
     __shared__ int flag;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kWarps); }
+        for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, s.release_all ? kThreads : kWarps); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -232,8 +232,12 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
             // MIO back-pressure: ~80 corrupted units per 1.5 M in K3 at the celeb shape, caught by
             // tests/test_fullsize_gpu.py. The ring is 5-6 stages deep, so holding a stage for one unit's
             // compute costs nothing measurable.
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
+            if (s.release_all) {
+                mbar_arrive(empty + stage);                      // every reader releases for itself
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);       // elected lane releases for its warp
+            }
             if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         if constexpr (Op::K > 0) {
@@ -254,6 +258,8 @@ static int launch_pipe(const typename Op::Params& p, RowWorkspace ws, long long 
         configured = true;
     }
     RowSched s = make_row_sched(B, D, W, Op::kOcc);
+    static const int release_all = env_int("SISS_RELEASE_ALL", 1);   // see the release note in pipe_row_kernel
+    s.release_all = release_all == 1 ? 1 : 0;
     pipe_row_kernel<Op><<<s.grid, kPipeThreads, smem, st>>>(p, ws, s);
     return (int)cudaGetLastError();
 }

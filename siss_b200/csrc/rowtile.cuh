@@ -31,6 +31,8 @@ struct RowSched {
     long long upr;   // units per row = ceil(D / W)
     long long U;     // total units = B * upr
     int grid;        // CTAs to launch
+    int release_all; // TMA ring: 1 = every consumer thread arrives on the stage's empty barrier itself,
+                     // 0 = one elected lane per warp arrives after __syncwarp (see bulkpipe.cuh)
     int nspans;      // contiguous spans the unit space is cut into. Currently == grid (span id == blockIdx.x).
                      // A dynamic span queue (several spans per CTA, claimed with atomicAdd) was built and
                      // measured in round 1: at the celeb shape a CTA has only ~14 stages of work, so the
@@ -65,6 +67,7 @@ inline RowSched make_row_sched(long long B, long long D, int W, int ctas_per_sm,
         if (ns > kMaxSpans) ns = kMaxSpans;
     }
     s.nspans = (int)ns;
+    s.release_all = 0;
     return s;
 }
 

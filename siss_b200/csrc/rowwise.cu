@@ -27,7 +27,7 @@ int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     if (!e || !*e) return dflt;
     const int v = std::atoi(e);
-    return v > 0 ? v : dflt;
+    return v >= 0 ? v : dflt;
 }
 
 // A/B switch for measurements: SISS_NO_TMA=1 forces the plain-LDG kernels on the vector path too.

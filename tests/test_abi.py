@@ -89,3 +89,41 @@ def test_scheduler_tables_match_oracle():
     g, sg = s.gamma_sigma("cpu")
     og, os_ = O.gamma_sigma(s.alphas_cumprod)
     assert torch.equal(g, og) and torch.equal(sg, os_)
+
+
+def test_argument_validation_without_a_gpu():
+    """Every entry point validates pointers / sizes / enums before it touches CUDA, so the error
+    behaviour of the ABI can be checked on a CPU box: SISS_EINVAL (-1), never a crash or a launch."""
+    from siss_b200 import _lib
+    lib = _lib.load()
+    N = None  # NULL
+    one = ctypes.c_void_p(16)  # a non-null, 16-byte aligned dummy address: never dereferenced on these paths
+    assert lib.siss_add_noise(N, one, one, one, 1000, one, 4, 16, 0, N) == -1
+    assert lib.siss_add_noise(one, one, one, one, 0, one, 4, 16, 0, N) == -1            # T < 1
+    assert lib.siss_add_noise(one, one, one, one, 1000, one, -1, 16, 0, N) == -1        # negative batch
+    assert lib.siss_add_noise(one, one, one, one, 1000, one, 0, 16, 0, N) == 0          # empty batch: no-op
+    assert lib.siss_add_noise(one, one, one, one, 1000, one, 4, 16, 7, N) == -2         # unknown dtype
+    assert lib.siss_add_noise_pair(one, N, one, one, one, 1000, one, one, 4, 16, 0, N) == -1
+    assert lib.siss_mixture_weights(one, one, one, one, one, one, one, one, 1000, 0.5, one, one, one, one, one, N,
+                                    4, 16, 0, N) == -1                                   # missing workspace
+    assert lib.siss_add_noise_mixture(one, one, one, one, one, one, one, one, 1000, 0.5, one, one, one, one, one, one,
+                                      4, 0, 0, N) == -1                                  # D < 1
+    assert lib.siss_wmse_fwd_bwd(one, 0, one, one, one, 0, one, one, one, 1000, one, one, 1.0, 1.0, one, N, one, one,
+                                 one, 4, 16, N) == -1
+    assert lib.siss_wmse_fwd_bwd(one, 1, one, one, one, 0, one, one, one, 1000, one, one, 1.0, 1.0, one, one, one, one,
+                                 one, 4, 16, N) == -2                                    # bf16 pred with fp32 latents
+    assert lib.siss_sqerr_fwd(one, 1, one, 2, one, N, 0.0, 16, N) == -2                  # bf16 x fp16 not compiled in
+    assert lib.siss_sqerr_bwd(one, 0, one, 0, N, 0, N, 0, 0.0, 0, one, 16, N) == -1      # no upstream gradient at all
+    assert lib.siss_norm3(N, one, 16, one, one, N) == -1
+    assert lib.siss_combine(one, one, one, 16, one, 3, 1.0, 1.0, 0, N, N) == -1          # bad mode
+    assert lib.siss_combine(one, one, one, 16, N, 0, 1.0, 1.0, 0, N, N) == -1            # sums3 missing
+    assert lib.siss_combine_adamw(one, one, 16, one, 0, 1.0, 1.0, 0, one, one, one, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1,
+                                  N, N, N) == -1                                         # step < 1
+    assert lib.siss_batch_stats(one, one, one, one, 0, 16, one, N) == -1                 # B < 1
+    arr = (ctypes.c_void_p * 8)(*[16 * (i + 1) for i in range(8)])
+    assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 3, 0, 16, one, one, one, one, N) == -2   # world must be 2, 4 or 8
+    assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 2, 2, 16, one, one, one, one, N) == -1   # rank out of range
+    assert lib.siss_p2p_combine_allgather(one, one, one, arr, 2, 0, 18, 0, 1.0, 1.0, 0, N, N) == -1  # shard % 4
+    assert lib.siss_mt_norm3(one, one, one, one, 0, 1, one, one, N) == -1                # no tensors
+    for code in (-1, -2, -3):
+        assert _lib.error_string(code).startswith("siss:")

@@ -131,7 +131,7 @@ def test_pipelined_kernels_are_deterministic_and_match_eager_at_full_size(env):
     e = env
     go = 1 / 64
     noise_f = e["noise"].float()
-    for it in range(4):
+    for it in range(24):
         a = ops.add_noise_pair(e["x0"], e["a0"], e["noise"], e["t"], e["ac"])
         f = ops.add_noise_mixture(e["x0"], e["a0"], e["noise"], e["keep"], e["t"], e["ac"], e["gamma"], e["sigma"], 0.5)
         k3 = ops.wmse_fwd_bwd(e["pred"], f[0], e["x0"], e["a0"], e["t"], e["gamma"], e["sigma"], f[3], f[4], go, go)
