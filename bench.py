@@ -89,6 +89,89 @@ class BenchUNet(torch.nn.Module):
         return (x.float() * self.scale + (self.bias + self.bank.sum() * 1e-6),)
 
 
+class StandInUNet(torch.nn.Module):
+    """Stand-in for diffusers.UNet2DModel in the supplementary steps/s measurement (diffusers is not
+    installed in this image): a small conv encoder/decoder with the UNet2DModel call convention, run under
+    bf16 autocast, plus a parameter bank that brings the parameter count to P so the gradient exchange and
+    the combine see the real buffer sizes. Its FLOPs are roughly two orders of magnitude below the real
+    113.67 M-parameter UNet at 256x256, so the share of the step spent in the exchange is an UPPER bound."""
+
+    def __init__(self, n_params: int, ch: int = 3, width: int = 48):
+        super().__init__()
+        C = torch.nn.Conv2d
+        self.inp = C(ch, width, 3, padding=1)
+        self.down = C(width, 2 * width, 3, stride=2, padding=1)
+        self.mid1 = C(2 * width, 2 * width, 3, padding=1)
+        self.mid2 = C(2 * width, 2 * width, 3, padding=1)
+        self.up = torch.nn.ConvTranspose2d(2 * width, width, 4, stride=2, padding=1)
+        self.out = C(width, ch, 3, padding=1)
+        self.temb = torch.nn.Embedding(1000, width)
+        own = sum(p.numel() for p in self.parameters())
+        self.bank = torch.nn.Parameter(torch.zeros(max(n_params - own, 1)))
+
+    def forward(self, x, timesteps, return_dict=False, **kw):
+        act = torch.nn.functional.silu
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            h = act(self.inp(x) + self.temb(timesteps)[:, :, None, None])
+            m = act(self.down(h))
+            m = act(self.mid2(act(self.mid1(m))))
+            h = h + act(self.up(m))
+            y = self.out(h)
+        return (y.float() + self.bank.sum() * 1e-6,)     # fp32 output, as accelerate's autocast wrapper returns
+
+
+def unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist):
+    """Supplementary: full unlearning optimiser steps (forward + two backward passes through a stand-in UNet,
+    SISS loss kernels, gradient exchange, fused combine + AdamW) through the public API, per-GPU batch 16,
+    data resident. Returns steps/s (max over ranks timing)."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.optim import FusedCombineAdamW
+    from siss_b200.step import UnlearnStep
+    Bs = 16
+    shape = (Bs, args.channels, args.res, args.res)
+    dt = torch_dtype(args.dtype)
+    torch.manual_seed(1234)                                   # identical initial weights on every rank
+    unet = StandInUNet(args.params, ch=args.channels).to(dev)
+    comb = GradCombiner(unet.parameters(), transport=args.transport)
+    opt = FusedCombineAdamW(comb, lr=5e-6, betas=(0.95, 0.999), eps=1e-8, weight_decay=1e-6)   # delete_celeb.yaml:127-134
+    step = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=Bs * n, lambd=0.5,
+                       scaling_norm=500.0, max_norm=1.0)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    x0 = (torch.rand(shape, device=dev, generator=g) * 2 - 1).to(dt)
+    a0 = (torch.rand(shape, device=dev, generator=g) * 2 - 1).to(dt)
+    keep = torch.rand(Bs, device=dev, generator=g) > 0.5
+
+    def one():
+        nz = torch.randn(shape, dtype=dt, device=dev)
+        ts = torch.randint(999, 1000, (Bs,), device=dev).long()
+        step.micro_step(x0, a0, nz, ts, keep_mask=keep)
+        step._micro = 0
+        opt.step(scaling_norm=500.0, max_norm=1.0)
+
+    for _ in range(3):
+        one()
+    barrier()
+    K = 10
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for _ in range(K):
+        one()
+    e_ev.record()
+    barrier()
+    el = torch.tensor([s_ev.elapsed_time(e_ev)], device=dev, dtype=torch.float64)
+    if n > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el.item()) / K
+    res = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "samples_per_s": Bs * n * 1e3 / ms, "per_gpu_batch": Bs,
+           "global_batch": Bs * n, "transport": comb.transport,
+           "note": ("SUPPLEMENTARY: full optimiser step through the public API (UnlearnStep + GradCombiner + "
+                    "FusedCombineAdamW) with a stand-in conv UNet (diffusers is not installed) carrying "
+                    f"P={args.params} parameters; not comparable with the real UNet's absolute steps/s")}
+    del unet, comb, opt, step
+    torch.cuda.empty_cache()
+    return res
+
+
 def synth_images(shape, dtype, seed):
     g = torch.Generator().manual_seed(seed)
     x0 = (torch.rand(shape, generator=g) * 2 - 1).to(dtype)  # data normalised to [-1, 1] (delete_celeb.yaml:28-34)
@@ -231,7 +314,9 @@ def workload_config(args, n):
         "latent_dtype": args.dtype, "pred_dtype": "fp32", "timesteps": "t=999 (delete_celeb.py:593)",
         "grad_params": args.params, "grad_accum": 1, "unet": "outside the path (resident eps_hat / P-param stub in e2e)",
         "parallelism": f"dp{n}", "transport": getattr(args, "_transport", "single" if n == 1 else "nccl"), "l2": "inputs larger than L2 (per-step footprint >> 126 MB); no flush",
-        "resident_step": "K1oK2 + K3 + K4a + K4b (+ reduce-scatter x2, scalar all-reduce, all-gather when N>1)",
+        "resident_step": ("K1oK2 + K3 + K4a + K4b; N>1: + gradient exchange — transport p2p = fused NVLink peer-memory "
+                          "kernels (reduce-scatter x2 + K4a | K4b + all-gather), transport nccl = reduce-scatter x2, "
+                          "3-scalar all-reduce, all-gather around K4a/K4b"),
     }
 
 
@@ -564,6 +649,13 @@ def run_siss(args):
                         "sample": (f"full workload per step (B={B}, P={P}), median of {len(times)} steps after 1 warm-up, "
                                    "oracle port of the reference loop in torch CPU")}
 
+    unlearn = None
+    if not args.no_extra_configs:
+        try:
+            torch.cuda.empty_cache()
+            unlearn = unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist)
+        except Exception as e:  # supplementary: never break the bench line
+            unlearn = {"error": repr(e)}
     others = None
     if rank == 0 and n == 1 and not args.no_extra_configs:
         torch.cuda.empty_cache()
@@ -574,7 +666,7 @@ def run_siss(args):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": sampler.summary(), "other_configs": others,
+            "clocks": sampler.summary(), "unlearn_steps": unlearn, "other_configs": others,
         }
         emit(line)
     if world > 1:

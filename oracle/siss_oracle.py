@@ -12,7 +12,7 @@ promotion and bf16 rounding are the reference's), of
     (third-party, pinned at environment.yml:232, NOT present under /root/reference and not
     installed here; restated from that release's published algorithm)     -> ``make_alphas_cumprod``, ``add_noise``
   * the inline two-backward + gradient-combine block, delete_celeb.py:682-767
-    (tshirt inf-guard delete_tshirt.py:688-690)                           -> ``reference_grad_step``
+    (tshirt inf-guard delete_tshirt.py:688-690)                           -> ``ReferenceGradLoop``, ``combine_flat``
   * ``accelerator.backward`` (loss / gradient_accumulation_steps, accelerate==0.27.2) and
     ``accelerator.clip_grad_norm_`` (= ``torch.nn.utils.clip_grad_norm_``, called directly).
 
