@@ -71,13 +71,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_step_equals_single_gpu():
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_step_equals_single_gpu(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + os.getpid() % 200
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29700 + os.getpid() % 200 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = q.get(timeout=300)
