@@ -270,6 +270,9 @@ int siss_batch_stats(const float* row_loss_x, const float* row_loss_a, const flo
  * order, writes the reduced shard to shard_x / shard_a (local), writes this rank's three partial sums
  * to sums3_local and to doubles [4*rank .. 4*rank+2] of every peer's scalar buffer h_peer_scalars[r]
  * (each at least 4*world doubles). Inbound NVLink bytes per rank: (world-1)/world * 8 per parameter.
+ * x_prereduced != 0: shard_x already holds the reduced G_x shard (its reduce-scatter was overlapped with
+ * the second backward pass, G_x being final after the first); only G_a crosses NVLink (4 B/parameter)
+ * and h_peers_x is ignored.
  *
  * siss_p2p_combine_allgather: K4b + all-gather in one kernel. Sums the `world` scalar slots (local
  * copy, rank order, so every rank derives identical s and clip), computes
@@ -280,7 +283,7 @@ int64_t siss_p2p_workspace_bytes(void);
 
 int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_peers_a,
                           double* const* h_peer_scalars, int world, int rank, int64_t shard_len,
-                          float* shard_x, float* shard_a, double* sums3_local,
+                          float* shard_x, float* shard_a, double* sums3_local, int x_prereduced,
                           void* workspace, siss_stream_t stream);
 
 int siss_p2p_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,

@@ -53,10 +53,12 @@ struct PeerOut {
 };
 
 // U float4 units per thread per iteration; WORLD x 2 x U 128-bit loads in flight per thread.
-template <int WORLD, int U>
+// X_PRE: the G_x shard was already reduced (early reduce-scatter overlapped with the second backward): x is
+// read from the local shard and only G_a crosses NVLink here.
+template <int WORLD, int U, bool X_PRE>
 __global__ void __launch_bounds__(kThreads, kP2POcc)
 p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* elements, % 4 == 0 */,
-                        float* __restrict__ shard_x, float* __restrict__ shard_a,
+                        float* shard_x, float* __restrict__ shard_a,
                         double* __restrict__ sums3_local, PeerOut pub, P2PWorkspace ws) {
     __shared__ double red[3 * kWarps];
     __shared__ int flag;
@@ -81,7 +83,8 @@ p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* element
             for (int u = 0; u < U; ++u) {
                 if (!ok[u]) continue;
                 const long long i = c * chunk + (long long)u * kThreads + threadIdx.x;
-                rx[r][u] = ldg_v4(peers.x[r] + base_elem + 4 * i);
+                if (!X_PRE) rx[r][u] = ldg_v4(peers.x[r] + base_elem + 4 * i);
+                else if (r == 0) rx[0][u] = ldg_v4(shard_x + 4 * i);
                 ra[r][u] = ldg_v4(peers.a[r] + base_elem + 4 * i);
             }
         }
@@ -95,12 +98,15 @@ p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* element
 #pragma unroll
             for (int r = 1; r < WORLD; ++r) {   // fixed rank order
                 float tx[4], ta[4];
-                VecTraits<float>::unpack(rx[r][u], tx);
+                if (!X_PRE) VecTraits<float>::unpack(rx[r][u], tx);
                 VecTraits<float>::unpack(ra[r][u], ta);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { sx[q] = __fadd_rn(sx[q], tx[q]); sa[q] = __fadd_rn(sa[q], ta[q]); }
+                for (int q = 0; q < 4; ++q) {
+                    if (!X_PRE) sx[q] = __fadd_rn(sx[q], tx[q]);
+                    sa[q] = __fadd_rn(sa[q], ta[q]);
+                }
             }
-            stg_stream(shard_x + 4 * i, VecTraits<float>::pack(sx));
+            if (!X_PRE) stg_stream(shard_x + 4 * i, VecTraits<float>::pack(sx));
             stg_stream(shard_a + 4 * i, VecTraits<float>::pack(sa));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -203,26 +209,35 @@ int64_t siss_p2p_workspace_bytes(void) { return 256 + (int64_t)kP2PMaxGrid * 3 *
 
 int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_peers_a, double* const* h_peer_scalars,
                           int world, int rank, int64_t shard_len, float* shard_x, float* shard_a,
-                          double* sums3_local, void* workspace, siss_stream_t stream) {
-    if (!h_peers_x || !h_peers_a || !h_peer_scalars || !shard_x || !shard_a || !sums3_local || !workspace) return SISS_EINVAL;
+                          double* sums3_local, int x_prereduced, void* workspace, siss_stream_t stream) {
+    if ((!x_prereduced && !h_peers_x) || !h_peers_a || !h_peer_scalars || !shard_x || !shard_a || !sums3_local || !workspace)
+        return SISS_EINVAL;
     if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || shard_len < 0 || shard_len % 4 != 0) return SISS_EINVAL;
     PeerPtrs peers{};
     PeerOut pub{};
     for (int r = 0; r < world; ++r) {
-        if (!h_peers_x[r] || !h_peers_a[r] || !h_peer_scalars[r]) return SISS_EINVAL;
-        if (!aligned16(h_peers_x[r]) || !aligned16(h_peers_a[r])) return SISS_EINVAL;
-        peers.x[r] = h_peers_x[r]; peers.a[r] = h_peers_a[r]; pub.scalars[r] = h_peer_scalars[r];
+        if ((!x_prereduced && !h_peers_x[r]) || !h_peers_a[r] || !h_peer_scalars[r]) return SISS_EINVAL;
+        if ((!x_prereduced && !aligned16(h_peers_x[r])) || !aligned16(h_peers_a[r])) return SISS_EINVAL;
+        peers.x[r] = x_prereduced ? nullptr : h_peers_x[r]; peers.a[r] = h_peers_a[r]; pub.scalars[r] = h_peer_scalars[r];
     }
     if (!aligned16(shard_x) || !aligned16(shard_a)) return SISS_EINVAL;
     P2PWorkspace ws = carve_p2p(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const long long nvec = shard_len / 4;
+#define SISS_P2P_REDUCE(WORLD_, U_)                                                                                     \
+    if (x_prereduced)                                                                                                  \
+        p2p_reduce_norm3_kernel<WORLD_, U_, true><<<p2p_grid(nvec, U_), kThreads, 0, st>>>(peers, rank, shard_len, shard_x,  \
+                                                                                            shard_a, sums3_local, pub, ws); \
+    else                                                                                                               \
+        p2p_reduce_norm3_kernel<WORLD_, U_, false><<<p2p_grid(nvec, U_), kThreads, 0, st>>>(peers, rank, shard_len, shard_x, \
+                                                                                             shard_a, sums3_local, pub, ws)
     switch (world) {
-        case 2: p2p_reduce_norm3_kernel<2, 4><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(peers, rank, shard_len, shard_x, shard_a, sums3_local, pub, ws); break;
-        case 4: p2p_reduce_norm3_kernel<4, 2><<<p2p_grid(nvec, 2), kThreads, 0, st>>>(peers, rank, shard_len, shard_x, shard_a, sums3_local, pub, ws); break;
-        case 8: p2p_reduce_norm3_kernel<8, 1><<<p2p_grid(nvec, 1), kThreads, 0, st>>>(peers, rank, shard_len, shard_x, shard_a, sums3_local, pub, ws); break;
+        case 2: SISS_P2P_REDUCE(2, 4); break;
+        case 4: SISS_P2P_REDUCE(4, 2); break;
+        case 8: SISS_P2P_REDUCE(8, 1); break;
         default: return SISS_EUNSUPPORTED;  // 2, 4 or 8 GPUs of one NVSwitch box
     }
+#undef SISS_P2P_REDUCE
     return (int)cudaGetLastError();
 }
 

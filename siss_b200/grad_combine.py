@@ -101,6 +101,9 @@ class GradCombiner:
             else:
                 self._shard_x = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
                 self._shard_a = torch.empty(self.shard_len, dtype=torch.float32, device=dev)
+        self._early_x = False   # G_x's reduce-scatter was already issued on the side stream (begin_a(last_micro_step=True))
+        self._side = None
+        self._early_done = None
         self._dirty_x = False  # G_x holds the previous combined gradient and must be cleared
         # compute back-ends: the CUDA kernels. (tests of the collective choreography on gloo/CPU
         # replace these two attributes with the oracle; the product has no other path.)
@@ -119,10 +122,26 @@ class GradCombiner:
             self._dirty_x = False
         self._point(self._views_x)
 
-    def begin_a(self) -> None:
+    def begin_a(self, last_micro_step: bool = False) -> None:
         """Call between the two backward passes: gradients now accumulate into ``G_a``. This is the
-        whole of delete_celeb.py:693-711 (clone, subtract, accumulate)."""
+        whole of delete_celeb.py:693-711 (clone, subtract, accumulate).
+
+        ``last_micro_step=True`` (data parallel only) says that ``G_x`` is now FINAL for this optimiser step —
+        the keep-term backward of the last accumulation micro-step has been enqueued — so its reduce-scatter is
+        issued right away on a side stream and overlaps with the second backward pass; :meth:`combine` then
+        only has to move ``G_a``. Do not accumulate further micro-steps into ``G_x`` after passing it."""
         self._point(self._views_a)
+        if last_micro_step and self.world > 1 and self.device.type == "cuda":
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._early_done = torch.cuda.Event()
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.device))      # backward #1 fully enqueued before this point
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ready)
+                dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+                self._early_done.record(self._side)
+            self._early_x = True
 
     # ------------------------------------------------------------------------------------------
     def combine(self, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
@@ -141,9 +160,14 @@ class GradCombiner:
             self._norm3(self.g_x, self.g_a, out=self.sums3)
             self._combine(self.g_x, self.g_a, self.sums3, mode, value, mn, inf_guard, out=self.g_x, stats=self.stats)
         elif self.peer is not None:
-            self.peer.combine(mode, value, mn, inf_guard, self.stats)
+            if self._early_x:
+                torch.cuda.current_stream(self.device).wait_event(self._early_done)
+            self.peer.combine(mode, value, mn, inf_guard, self.stats, x_prereduced=self._early_x)
         else:
-            dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+            if self._early_x:
+                torch.cuda.current_stream(self.device).wait_event(self._early_done)
+            else:
+                dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
             dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
             self._norm3(self._shard_x, self._shard_a, out=self.sums3)
             dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)  # the scalar-norm all-reduce
@@ -152,6 +176,7 @@ class GradCombiner:
             dist.all_gather_into_tensor(self.g_x, self._shard_x, group=self.group)
         self.g_a.zero_()
         self._dirty_x = True
+        self._early_x = False
         self._point(self._views_x)
         return self.stats
 

@@ -52,15 +52,19 @@ class PeerExchange:
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)
 
-    def combine(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor) -> None:
-        """Result lands in every rank's ``g_x``. Stream-ordered; no host synchronisation."""
+    def combine(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
+                x_prereduced: bool = False) -> None:
+        """Result lands in every rank's ``g_x``. Stream-ordered; no host synchronisation. With
+        ``x_prereduced`` the reduced ``G_x`` shard is already in ``shard_x`` (early reduce-scatter overlapped
+        with the second backward) and only ``G_a`` crosses NVLink in the first kernel."""
         from . import ops
         lib = _lib.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.h_x.barrier(channel=0)        # every rank's G_x / G_a are complete
         _lib.check(lib.siss_p2p_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
                                              self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                             self.sums_local.data_ptr(), self.ws.data_ptr(), stream),
+                                             self.sums_local.data_ptr(), int(bool(x_prereduced)), self.ws.data_ptr(),
+                                             stream),
                    "siss_p2p_reduce_norm3")
         self.h_x.barrier(channel=1)        # every rank's scalar slot has been written everywhere
         _lib.check(lib.siss_p2p_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),

@@ -71,14 +71,16 @@ class UnlearnStep:
 
     # ------------------------------------------------------------------------------------------
     def micro_step(self, x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
-                   conditioning: Optional[dict] = None, keep_mask: Optional[torch.Tensor] = None
-                   ) -> Dict[str, torch.Tensor]:
+                   conditioning: Optional[dict] = None, keep_mask: Optional[torch.Tensor] = None,
+                   forget_target: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Forward + both backward passes for one micro-batch. Returns per-sample device tensors:
         ``row_loss_x`` / ``row_loss_a`` (sum over C,H,W of the unweighted squared errors) and, for SISS,
-        ``w_x`` / ``w_a`` / ``dist_x`` / ``dist_a``."""
+        ``w_x`` / ``w_a`` / ``dist_x`` / ``dist_a``. ``forget_target`` (EraseDiff only) replaces the uniform draw
+        of ddpm_deletion_loss.py:75 with a given tensor — for reproducible tests and replays."""
         cond = conditioning or {}
         out: Dict[str, torch.Tensor] = {}
         cb = self.combiner
+        last = self._micro == self.G - 1          # last accumulation micro-step of this optimiser step
         if self.loss_fn == "importance_sampling_with_mixture":
             keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
             x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
@@ -88,7 +90,7 @@ class UnlearnStep:
                                                     w_x, w_a, self.go, self.go)
             cb.begin_x()
             torch.autograd.backward(pred, g_x, retain_graph=True)
-            cb.begin_a()
+            cb.begin_a(last_micro_step=last)      # data parallel: G_x's reduce-scatter overlaps backward #2
             torch.autograd.backward(pred, g_a)
             out.update(w_x=w_x, w_a=w_a, dist_x=d_x, dist_a=d_a, row_loss_x=rl_x, row_loss_a=rl_a)
         elif self.loss_fn in ("double_forward_with_neg_del", "erasediff"):
@@ -96,7 +98,10 @@ class UnlearnStep:
             pred_x = self.unet(xt_x, timesteps, **cond, return_dict=False)[0]
             pred_a = self.unet(xt_a, timesteps, **cond, return_dict=False)[0]
             # EraseDiff's forget target: uniform noise drawn after the second forward (ddpm_deletion_loss.py:75)
-            tgt_a = torch.rand_like(pred_a) if self.loss_fn == "erasediff" else noise
+            if self.loss_fn == "erasediff":
+                tgt_a = torch.rand_like(pred_a) if forget_target is None else forget_target
+            else:
+                tgt_a = noise
             tgt_x = noise
             if tgt_a.dtype != tgt_x.dtype:
                 tgt_x = tgt_x.to(tgt_a.dtype)
@@ -104,7 +109,7 @@ class UnlearnStep:
                                                         self.go, self.go)
             cb.begin_x()
             torch.autograd.backward(pred_x, g_x)
-            cb.begin_a()
+            cb.begin_a(last_micro_step=last)
             torch.autograd.backward(pred_a, g_a)
             out.update(row_loss_x=rl_x, row_loss_a=rl_a)
         else:

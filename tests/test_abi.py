@@ -121,8 +121,8 @@ def test_argument_validation_without_a_gpu():
                                   N, N, N) == -1                                         # step < 1
     assert lib.siss_batch_stats(one, one, one, one, 0, 16, one, N) == -1                 # B < 1
     arr = (ctypes.c_void_p * 8)(*[16 * (i + 1) for i in range(8)])
-    assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 3, 0, 16, one, one, one, one, N) == -2   # world must be 2, 4 or 8
-    assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 2, 2, 16, one, one, one, one, N) == -1   # rank out of range
+    assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 3, 0, 16, one, one, one, 0, one, N) == -2   # world must be 2, 4 or 8
+    assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 2, 2, 16, one, one, one, 0, one, N) == -1   # rank out of range
     assert lib.siss_p2p_combine_allgather(one, one, one, arr, 2, 0, 18, 0, 1.0, 1.0, 0, N, N) == -1  # shard % 4
     assert lib.siss_mt_norm3(one, one, one, one, 0, 1, one, one, N) == -1                # no tensors
     for code in (-1, -2, -3):

@@ -321,3 +321,34 @@ def test_fused_combine_adamw_matches_reference_loop_plus_torch_adamw(loss_fn, kw
         for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
             assert p.data_ptr() >= opt.p_flat.data_ptr()                                    # params live in the flat buffer
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=3e-5, atol=3e-6)
+
+
+@pytest.mark.parametrize("G", [1, 2])
+def test_unlearn_step_erasediff_matches_reference_loop(G, dev):
+    """EraseDiff on the fast path (dual-MSE kernel, eta-mode combine: s = -max(eta - <X,A>/||A||^2, 0),
+    delete_celeb.py:741-742) vs the reference loop, sharing the uniform forget target explicitly."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    B, eta = 4, 0.05
+    cpu_net = TinyNet(); gpu_net = copy.deepcopy(cpu_net).to(dev)
+    sched = SissDDPMScheduler()
+    oloss = O.OracleDeletionLoss(*O.gamma_sigma(sched.alphas_cumprod))
+    loop = O.ReferenceGradLoop(cpu_net, train_batch_size=B, grad_accum_steps=G)
+    comb = GradCombiner(gpu_net.parameters())
+    step = UnlearnStep(gpu_net, sched, comb, loss_fn="erasediff", train_batch_size=B, gradient_accumulation_steps=G,
+                       eta=eta, max_norm=1.0)
+    torch.manual_seed(3)
+    for k in range(G):
+        x0, a0 = torch.rand(B, 1, 8, 8) * 2 - 1, torch.rand(B, 1, 8, 8) * 2 - 1
+        noise, t, u = torch.randn(B, 1, 8, 8), torch.randint(300, 1000, (B,)), torch.rand(B, 1, 8, 8)
+        all_d = {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)}
+        del_d = {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}
+        loop.micro_step(oloss.erasediff(cpu_net, t, noise, {}, all_d, del_d, uniform_noise=u), retain_graph=False)
+        step.micro_step(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev), forget_target=u.to(dev))
+    ref = loop.sync_step(False, "erasediff", eta=eta, max_norm=1.0)
+    stats = step.sync_step().cpu()
+    torch.testing.assert_close(stats[2], ref["scaling_factor"].float(), rtol=2e-3, atol=1e-5)
+    for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
+        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-3, atol=2e-6)

@@ -29,7 +29,7 @@ stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 def reduce_k():
     _lib.check(lib.siss_p2p_reduce_norm3(pe.ptrs_x, pe.ptrs_a, pe.ptrs_s, world, rank, pe.shard_len, pe.shard_x.data_ptr(),
-                                         pe.shard_a.data_ptr(), pe.sums_local.data_ptr(), pe.ws.data_ptr(), stream), "reduce")
+                                         pe.shard_a.data_ptr(), pe.sums_local.data_ptr(), 0, pe.ws.data_ptr(), stream), "reduce")
 
 
 def gather_k():
