@@ -237,13 +237,19 @@ int siss_mt_combine(const float* const* d_gx, const float* const* d_ga, float* c
  *   sums3 == NULL        : no combine scalars — g = g_x (already combined / exchanged), no clip;
  *   mode == SISS_COMBINE_NONE : single-term methods, g = clip * g_x (g_a may be NULL);
  *   grad_out (nullable)  : also materialise g (may alias g_x), e.g. for logging or a later hook;
- *   step                 : 1-based optimiser step count (bias corrections 1 - beta^step).
+ *   step                 : 1-based optimiser step count (bias corrections 1 - beta^step);
+ *   d_step (nullable)    : if given, the step count is read from this DEVICE int64 instead (and `step` is
+ *                          ignored), so a captured CUDA graph stays valid across optimiser steps; advance it
+ *                          on the stream with siss_counter_add before the call.
  * 40 bytes/parameter (5 reads + 5 writes) instead of 48 in 4 launches for K4b + AdamW + 2 memsets.
  * ---------------------------------------------------------------------------------------- */
 int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const double* sums3, int mode, float value,
                        float max_norm, int inf_guard, float* param, float* exp_avg, float* exp_avg_sq,
                        double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                       int zero_grads, float* grad_out, float* stats5, siss_stream_t stream);
+                       const int64_t* d_step, int zero_grads, float* grad_out, float* stats5, siss_stream_t stream);
+
+/* *d_counter += value, stream-ordered (one thread). For the device-side optimiser step count. */
+int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused statistics epilogue — the per-batch logging scalars of delete_celeb.py:626-656 (mean over

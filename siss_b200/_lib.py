@@ -45,7 +45,8 @@ SIGNATURES = {
     "siss_mt_chunk_elems": (_I, []),
     "siss_mt_norm3": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "siss_mt_combine": (_I, [_P, _P, _P, _P, _P, _I, _L, _P, _I, _F, _F, _I, _P, _P]),
-    "siss_combine_adamw": (_I, [_P, _P, _L, _P, _I, _F, _F, _I, _P, _P, _P, _D, _D, _D, _D, _D, _L, _I, _P, _P, _P]),
+    "siss_combine_adamw": (_I, [_P, _P, _L, _P, _I, _F, _F, _I, _P, _P, _P, _D, _D, _D, _D, _D, _L, _P, _I, _P, _P, _P]),
+    "siss_counter_add": (_I, [_P, _L, _P]),
     "siss_batch_stats": (_I, [_P, _P, _P, _P, _L, _L, _P, _P]),
     "siss_p2p_workspace_bytes": (_L, []),
     "siss_p2p_reduce_norm3": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _I, _P, _P]),

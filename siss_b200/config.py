@@ -92,7 +92,8 @@ def step_from_config(cfg: Dict[str, Any], unet, scheduler, combiner, max_norm: f
                        superfactor=hp["superfactor"],
                        scaling_norm=hp["scaling_norm"] if fn in ("importance_sampling_with_mixture",
                                                                  "double_forward_with_neg_del") else None,
-                       eta=hp["eta"] if fn == "erasediff" else None, max_norm=max_norm, inf_guard=inf_guard)
+                       eta=hp["eta"] if fn == "erasediff" else None, max_norm=max_norm, inf_guard=inf_guard,
+                       superfactor_decay=hp["superfactor_decay"])
 
 
 def adamw_kwargs(cfg: Dict[str, Any]) -> Dict[str, Any]:

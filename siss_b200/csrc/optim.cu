@@ -28,7 +28,18 @@ struct AdamScalars {
     float bc2_sqrt;     // sqrt(1 - beta2^t)
     float neg_step;     // -lr / (1 - beta1^t)
     float eps;
+    double lr, beta1_d, beta2_d;   // for the device-side step counter variant
 };
+
+// Bias corrections from a step count held in DEVICE memory (so a captured CUDA graph stays valid from one
+// optimiser step to the next): same double-precision expressions the host path evaluates.
+__device__ __forceinline__ void adam_bias_from_step(AdamScalars& a, long long step) {
+    const double bc1 = 1.0 - pow(a.beta1_d, (double)step), bc2 = 1.0 - pow(a.beta2_d, (double)step);
+    a.bc2_sqrt = (float)sqrt(bc2);
+    a.neg_step = (float)(-(a.lr / bc1));
+}
+
+__global__ void counter_add_kernel(long long* p, long long v) { *p += v; }
 
 __device__ __forceinline__ void adam_update(float g, float& p, float& m, float& v, const AdamScalars& a) {
     p = __fmul_rn(p, a.decay);
@@ -43,7 +54,9 @@ __global__ void __launch_bounds__(kThreads, kOptOcc)
 combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n, long long nvec,
                      const double* __restrict__ sums3, int mode, float value, float max_norm, int inf_guard,
                      float* __restrict__ param, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                     AdamScalars as, int zero_grads, float* __restrict__ grad_out, float* __restrict__ stats5) {
+                     AdamScalars as, const long long* __restrict__ d_step, int zero_grads,
+                     float* __restrict__ grad_out, float* __restrict__ stats5) {
+    if (d_step != nullptr) adam_bias_from_step(as, *d_step);   // step count from device memory (graph replay)
     float s = 0.f, clip = 1.f;
     if (sums3 != nullptr) {
         const CombineScalars cs = combine_scalars_from(sums3[0], sums3[1], sums3[2], mode, value, max_norm, inf_guard,
@@ -115,11 +128,18 @@ combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n
 
 using namespace siss;
 
+extern "C" int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t stream) {
+    if (!d_counter) return SISS_EINVAL;
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)d_counter, (long long)value);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const double* sums3, int mode, float value,
                                   float max_norm, int inf_guard, float* param, float* exp_avg, float* exp_avg_sq,
                                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                                  int zero_grads, float* grad_out, float* stats5, siss_stream_t stream) {
-    if (!g_x || !param || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return SISS_EINVAL;
+                                  const int64_t* d_step, int zero_grads, float* grad_out, float* stats5,
+                                  siss_stream_t stream) {
+    if (!g_x || !param || !exp_avg || !exp_avg_sq || n < 0 || (step < 1 && !d_step)) return SISS_EINVAL;
     if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_NONE) return SISS_EINVAL;
     const bool two_term = (g_a != nullptr) && mode != SISS_COMBINE_NONE;
     if (mode != SISS_COMBINE_NONE && (!g_a || !sums3)) return SISS_EINVAL;
@@ -129,10 +149,13 @@ extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const doubl
     as.w1 = (float)(1.0 - beta1);
     as.beta2 = (float)beta2;
     as.w2 = (float)(1.0 - beta2);
-    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    const double hstep = (double)(step < 1 ? 1 : step);
+    const double bc1 = 1.0 - pow(beta1, hstep), bc2 = 1.0 - pow(beta2, hstep);
     as.bc2_sqrt = (float)sqrt(bc2);
     as.neg_step = (float)(-(lr / bc1));
     as.eps = (float)eps;
+    as.lr = lr; as.beta1_d = beta1; as.beta2_d = beta2;
+    const long long* dstep = (const long long*)d_step;
     bool al = aligned16(g_x) && aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(grad_out);
     if (two_term) al = al && aligned16(g_a);
     const long long nvec = al ? n / 4 : 0;
@@ -148,9 +171,9 @@ extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     if (two_term)
         combine_adamw_kernel<true><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,
-                                                                   param, exp_avg, exp_avg_sq, as, zero_grads, grad_out, stats5);
+                                                                   param, exp_avg, exp_avg_sq, as, dstep, zero_grads, grad_out, stats5);
     else
         combine_adamw_kernel<false><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,
-                                                                    param, exp_avg, exp_avg_sq, as, zero_grads, grad_out, stats5);
+                                                                    param, exp_avg, exp_avg_sq, as, dstep, zero_grads, grad_out, stats5);
     return (int)cudaGetLastError();
 }

@@ -36,19 +36,24 @@ class FusedCombineAdamW:
         self.exp_avg = torch.zeros_like(self.p_flat)
         self.exp_avg_sq = torch.zeros_like(self.p_flat)
         self.step_count = 0
+        # the step count also lives on the device and is advanced on the stream, so that a CUDA graph captured
+        # around step() applies the right bias corrections on every replay
+        self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def _launch(self, sums3: Optional[torch.Tensor], mode: int, value: float, max_norm: float, inf_guard: bool,
                 two_term: bool) -> None:
         cb = self.combiner
         self.step_count += 1
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().siss_counter_add(ctypes.c_void_p(self.d_step.data_ptr()), 1, stream), "siss_counter_add")
         _lib.check(_lib.load().siss_combine_adamw(
             ctypes.c_void_p(cb.g_x.data_ptr()), ctypes.c_void_p(cb.g_a.data_ptr() if two_term else 0), cb.total,
             ctypes.c_void_p(0 if sums3 is None else sums3.data_ptr()), int(mode), float(value), float(max_norm),
             int(bool(inf_guard)), ctypes.c_void_p(self.p_flat.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
             ctypes.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
-            self.weight_decay, self.step_count, 1, ctypes.c_void_p(0), ctypes.c_void_p(cb.stats.data_ptr()),
-            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "siss_combine_adamw")
-        ops._count()
+            self.weight_decay, self.step_count, ctypes.c_void_p(self.d_step.data_ptr()), 1, ctypes.c_void_p(0),
+            ctypes.c_void_p(cb.stats.data_ptr()), stream), "siss_combine_adamw")
+        ops._count(2)
 
     def step(self, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
              max_norm: Optional[float] = 1.0, inf_guard: bool = False, single_term: bool = False) -> torch.Tensor:

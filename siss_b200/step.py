@@ -46,7 +46,8 @@ class UnlearnStep:
                  loss_fn: str = "importance_sampling_with_mixture", train_batch_size: int,
                  gradient_accumulation_steps: int = 1, lambd: Optional[float] = None,
                  superfactor: Optional[float] = None, scaling_norm: Optional[float] = None,
-                 eta: Optional[float] = None, max_norm: Optional[float] = 1.0, inf_guard: bool = False):
+                 eta: Optional[float] = None, max_norm: Optional[float] = 1.0, inf_guard: bool = False,
+                 superfactor_decay: Optional[float] = None):
         if loss_fn not in TWO_TERM + ONE_TERM:
             raise ValueError(f"unknown loss_fn {loss_fn!r}")
         if loss_fn == "importance_sampling_with_mixture" and lambd is None:
@@ -62,6 +63,9 @@ class UnlearnStep:
         self.train_batch_size = int(train_batch_size)
         self.G = int(gradient_accumulation_steps)
         self.lambd, self.superfactor = lambd, superfactor
+        # `deletion.superfactor_decay`: the reference multiplies loss_params.superfactor by it after every
+        # micro-step's statistics (delete_celeb.py:658-662), i.e. the NEXT micro-step sees the decayed value
+        self.superfactor_decay = superfactor_decay
         self.scaling_norm, self.eta, self.max_norm, self.inf_guard = scaling_norm, eta, max_norm, inf_guard
         self.go = upstream_scale(self.train_batch_size, self.G)
         dev = combiner.device
@@ -127,6 +131,8 @@ class UnlearnStep:
             cb.begin_x()
             torch.autograd.backward(pred, g)
             out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl
+        if self.superfactor is not None and self.superfactor_decay is not None:
+            self.superfactor *= self.superfactor_decay
         self._micro += 1
         return out
 

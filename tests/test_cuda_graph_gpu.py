@@ -87,8 +87,6 @@ def test_optimizer_step_is_graph_capturable(cuda_device, fused_opt):
     # capture does not execute: replay for seed 11, then seed 12
     for i, seed in enumerate((11, 12), start=1):
         fill(seed)
-        if opt_g is not None:
-            pass  # bias-correction step count is baked at capture (step 2); see note below
         graph.replay()
         torch.cuda.synchronize()
         torch.testing.assert_close(s_static, eager[i][0], rtol=1e-5, atol=1e-6, equal_nan=True)
@@ -96,8 +94,9 @@ def test_optimizer_step_is_graph_capturable(cuda_device, fused_opt):
             torch.testing.assert_close(gs_static, eager[i][1], rtol=1e-4, atol=1e-7)
             got = torch.cat([p.grad.reshape(-1) for p in net_g.parameters()])
             torch.testing.assert_close(got, eager[i][2], rtol=2e-4, atol=1e-6)
-        elif i == 1:
-            # fused AdamW: hyper-parameters incl. the step count are kernel ARGUMENTS, hence frozen in the
-            # graph; the first replay (optimiser step 2) must match eager exactly in its update.
+        else:
+            # fused AdamW: the step count lives in device memory and is advanced inside the graph
+            # (siss_counter_add), so EVERY replay applies the bias corrections of its own optimiser step.
             got = torch.cat([p.detach().reshape(-1) for p in net_g.parameters()])
             torch.testing.assert_close(got, eager[i][3], rtol=1e-5, atol=1e-6)
+            assert int(opt_g.d_step.item()) == i + 1
