@@ -352,3 +352,32 @@ def test_unlearn_step_erasediff_matches_reference_loop(G, dev):
     torch.testing.assert_close(stats[2], ref["scaling_factor"].float(), rtol=2e-3, atol=1e-5)
     for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
         torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-3, atol=2e-6)
+
+
+def test_device_feeder_orders_and_protects_slots(dev):
+    """Double-buffered pinned->device feeding: batches come out in submission order with the right contents
+    even though the copy of batch i+1 is in flight while batch i is being read, and a slot is never
+    overwritten before the compute that read it has been enqueued past it."""
+    from siss_b200.feed import DeviceFeeder
+    shape = (8, 3, 64, 64)
+    feeder = DeviceFeeder([shape, shape], [torch.bfloat16, torch.bfloat16], dev, depth=2)
+    hosts = [((torch.full(shape, float(i)).bfloat16()).pin_memory(), (torch.full(shape, float(-i)).bfloat16()).pin_memory())
+             for i in range(7)]
+    feeder.submit(hosts[0])
+    sums = []
+    for i in range(7):
+        x, a = feeder.next()
+        if i + 1 < 7:
+            feeder.submit(hosts[i + 1])
+        # a long-ish consumer of the slot on the compute stream
+        acc = x.float()
+        for _ in range(20):
+            acc = acc * 1.0 + 0.0
+        sums.append((acc.mean() + a.float().mean() * 1000).reshape(1))
+    got = torch.cat(sums).cpu()
+    exp = torch.tensor([i - 1000.0 * i for i in range(7)])
+    torch.testing.assert_close(got, exp, rtol=0, atol=0)
+    with pytest.raises(RuntimeError):
+        feeder.next()                                   # nothing submitted
+    with pytest.raises(ValueError):
+        feeder.submit([torch.zeros(shape).bfloat16(), torch.zeros(shape).bfloat16()])   # not pinned

@@ -32,6 +32,32 @@ def _batch(Bg):
             torch.randn(Bg, 1, 16, 16, generator=g), torch.randint(300, 1000, (Bg,), generator=g))
 
 
+def _run_opt(rank, world, Bg, transport="auto"):
+    """Three optimiser steps with the fused combine+AdamW under data parallel; returns the final parameters."""
+    from siss_b200 import parallel
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.optim import FusedCombineAdamW
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda", rank if world > 1 else 0)
+    net = TinyNet().to(dev)
+    comb = GradCombiner(net.parameters(), transport=transport)
+    opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2)
+    step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
+                       train_batch_size=Bg, lambd=0.5, scaling_norm=5.0, max_norm=1.0)
+    torch.manual_seed(23)
+    for it in range(3):
+        x0, a0, noise, t = _batch(Bg)
+        keep = parallel.global_keep_mask(Bg, 0.5, rank, world)
+        sh = lambda v: parallel.shard_rows(v, rank, world).to(dev)
+        step.micro_step(sh(x0 + 0.02 * it), sh(a0), sh(noise), sh(t), keep_mask=keep)
+        step._micro = 0
+        opt.step(scaling_norm=5.0, max_norm=1.0)
+    torch.cuda.synchronize()
+    return torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
+
+
 def _run(rank, world, Bg, G, transport="auto"):
     from siss_b200 import parallel
     from siss_b200.grad_combine import GradCombiner
@@ -65,6 +91,8 @@ def _worker(rank, world, port, q):
     out = {}
     for transport in ("nccl", "p2p"):
         out[transport] = _run(rank, world, 8, 2, transport)
+        if world == 2:
+            out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
     if rank == 0:
         q.put(out)
     dist.barrier()
@@ -86,6 +114,11 @@ def test_multi_gpu_step_equals_single_gpu(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     flat1, stats1 = _run(0, 1, 8, 2)
-    for transport, (flat2, stats2) in out.items():      # NCCL collectives and fused NVLink peer-memory kernels
+    params1 = _run_opt(0, 1, 8) if world == 2 else None
+    for transport, res in out.items():                  # NCCL collectives and fused NVLink peer-memory kernels
+        if transport.endswith("/fused_adamw"):
+            torch.testing.assert_close(res, params1, rtol=3e-5, atol=3e-6, msg=lambda m: f"{transport}: {m}")
+            continue
+        flat2, stats2 = res
         torch.testing.assert_close(flat2, flat1, rtol=2e-4, atol=2e-6, msg=lambda m: f"{transport}: {m}")
         torch.testing.assert_close(stats2, stats1, rtol=2e-4, atol=1e-7, msg=lambda m: f"{transport}: {m}")
