@@ -19,7 +19,7 @@
 
 namespace siss {
 
-constexpr int kPipeThreads = kThreads + 32;  // 8 consumer warps + 1 producer warp
+constexpr int kPipeThreads = kThreads + 64;  // 8 consumer warps + 1 producer warp + 1 reducer warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,42 +80,59 @@ __device__ __forceinline__ void consumer_block_sum(float (&v)[K], float* smem) {
     }
 }
 
-// row_reduce for the consumer threads of a pipelined kernel (see rowtile.cuh::row_reduce).
-template <int K>
-__device__ __forceinline__ bool consumer_row_reduce(float (&acc)[K], double (&tot)[K], const RowSched& s,
-                                                    const RowWorkspace& ws, long long row, bool row_began_before_span,
-                                                    float* red, int* flag) {
-    static_assert(K <= 3, "slot holds 3 values");
-    consumer_block_sum<K>(acc, red);
+// ------------------------------------------------------------------------------------------------
+// Row-segment reduction off the consumers' critical path.
+//
+// Per segment every consumer warp reduces its K sums with shuffles and lane 0 drops them into a small
+// shared-memory ring slot (red_full mbarrier, count = kWarps). A dedicated REDUCER warp picks the slot up,
+// adds the eight warp partials in fixed order and does everything that used to stall the whole CTA:
+// partial-slot publish, device fence, per-row ticket, and — if it is the last contributor — the fixed-order
+// cross-CTA combine and the row epilogue. The reducer has no data stores in flight, so its fence is cheap,
+// and the consumers go straight on to their next stage: no bar.sync, no fence, no atomics on their path.
+// (Measured before this change: making spans shorter — dynamic queue or oversubscribed grid — made K1oK2
+// SLOWER, 34 vs 30 us, because each span end cost all 256 consumer threads a fence round trip.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kRedSlots = 4;
+constexpr int kRedStride = 4;   // floats per (slot, warp)
+
+template <class Op>
+__device__ __forceinline__ void reducer_segment(const typename Op::Params& p, const RowSched& s, const RowWorkspace& ws,
+                                                long long row, bool row_began_before_span,
+                                                const float (&part)[Op::K ? Op::K : 1]) {
+    constexpr int K = Op::K;
+    static_assert(K >= 1 && K <= 3, "slot holds 3 values");
+    const int lane = threadIdx.x & 31;
+    const typename Op::Row r = Op::row_begin(p, row);
     const long long rs = row * s.upr;
     const int first = span_owner(s, rs), last = span_owner(s, rs + s.upr - 1);
+    double tot[K];
     if (first == last) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) tot[k] = (double)acc[k];
-        return threadIdx.x < 32;
-    }
-    if (threadIdx.x == 0) {
-        st_slot(ws.partials + partial_slot(blockIdx.x, row_began_before_span) * kRowPartialStride, acc[0],
-                K > 1 ? acc[1] : 0.f, K > 2 ? acc[2] : 0.f);
-        __threadfence();
-        unsigned int* counter = ws.counters + 1 + row;
-        const unsigned int tk = atomicAdd(counter, 1u);
-        const int is_last = (tk == (unsigned)(last - first));
-        if (is_last) *counter = 0u;
-        *flag = is_last;
-    }
-    consumer_sync();
-    if (*flag == 0 || threadIdx.x >= 32) return false;
-    __threadfence();
-    double t[3] = {0.0, 0.0, 0.0};
-    const int n = last - first + 1;
-    for (int i = threadIdx.x; i < n; i += 32) {   // contributors are the consecutive spans first..last
-        const float4 v = ld_slot(ws.partials + partial_slot(first + i, i != 0) * kRowPartialStride);
-        t[0] += (double)v.x; t[1] += (double)v.y; t[2] += (double)v.z;
-    }
+        for (int k = 0; k < K; ++k) tot[k] = (double)part[k];
+    } else {
+        int is_last = 0;
+        if (lane == 0) {
+            st_slot(ws.partials + partial_slot(blockIdx.x, row_began_before_span) * kRowPartialStride, part[0],
+                    K > 1 ? part[1] : 0.f, K > 2 ? part[2] : 0.f);
+            __threadfence();
+            unsigned int* counter = ws.counters + 1 + row;
+            const unsigned int tk = atomicAdd(counter, 1u);
+            is_last = (tk == (unsigned)(last - first));
+            if (is_last) *counter = 0u;         // leave the workspace clean for the next launch
+        }
+        is_last = __shfl_sync(0xffffffffu, is_last, 0);
+        if (!is_last) return;
+        __threadfence();                        // acquire side
+        double t[3] = {0.0, 0.0, 0.0};
+        const int n = last - first + 1;
+        for (int i = lane; i < n; i += 32) {    // contributors are the consecutive spans first..last
+            const float4 v = ld_slot(ws.partials + partial_slot(first + i, i != 0) * kRowPartialStride);
+            t[0] += (double)v.x; t[1] += (double)v.y; t[2] += (double)v.z;
+        }
 #pragma unroll
-    for (int k = 0; k < K; ++k) tot[k] = warp_sum(t[k]);
-    return true;
+        for (int k = 0; k < K; ++k) tot[k] = warp_sum(t[k]);
+    }
+    if (lane == 0) Op::row_end(p, r, row, tot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -134,6 +151,8 @@ __device__ __forceinline__ bool consumer_row_reduce(float (&acc)[K], double (&to
 //                               float (&acc)[K ? K : 1])      compute + global stores for one unit
 //   __device__ static void row_end(const Params&, const Row&, long long row, const double (&tot)[K ? K : 1])
 // `unit_index` is the global unit number (row * upr + u); element offset = unit_index * W.
+//
+// Warp roles: 0..7 consumers, 8 producer (one elected lane issues the bulk copies), 9 reducer.
 // ------------------------------------------------------------------------------------------------
 template <class Op>
 struct PipeSmem {
@@ -147,7 +166,10 @@ struct PipeSmem {
         for (int j = 0; j < i; ++j) b += Op::ub(j) * kThreads;
         return b;
     }
-    __host__ __device__ static constexpr int bytes() { return Op::kStages * stage_bytes() + 2 * Op::kStages * 8 + 64; }
+    __host__ __device__ static constexpr int bytes() {
+        return Op::kStages * stage_bytes() + 2 * Op::kStages * 8 + 2 * kRedSlots * 8 +
+               kRedSlots * kWarps * kRedStride * 4 + 64;
+    }
 };
 
 template <class Op>
@@ -159,11 +181,13 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
     unsigned char* stage_mem = smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + S * SB);
     uint64_t* empty = full + S;
-    __shared__ float red[3 * kWarps];
-    __shared__ int flag;
+    uint64_t* red_full = empty + S;
+    uint64_t* red_empty = red_full + kRedSlots;
+    float* red_buf = reinterpret_cast<float*>(red_empty + kRedSlots);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, s.release_all ? kThreads : kWarps); }
+        for (int i = 0; i < kRedSlots; ++i) { mbar_init(red_full + i, kWarps); mbar_init(red_empty + i, 1); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -171,10 +195,12 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
     long long u0, u1;
     cta_span(s, u0, u1);
     if (u0 >= u1) return;
-    const bool is_producer = threadIdx.x >= kThreads;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 
-    if (is_producer) {
-        if (threadIdx.x != kThreads) return;  // one elected thread issues all copies
+    if (warp == kWarps) {
+        // ---------------------------------------------------------------- producer (one elected thread)
+        if (lane != 0) return;
         int stage = 0;
         uint32_t phase = 0;
         for (long long row = u0 / s.upr; row * s.upr < u1; ++row) {
@@ -201,10 +227,40 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
         return;
     }
 
-    // ---------------------------------------------------------------- consumers (threads 0..255)
+    if (warp == kWarps + 1) {
+        // ---------------------------------------------------------------- reducer warp
+        if constexpr (Op::K > 0) {
+            int rslot = 0;
+            uint32_t rphase = 0;
+            for (long long row = u0 / s.upr; row * s.upr < u1; ++row) {
+                const RowSeg seg = row_segment(s, u0, u1, row);
+                mbar_wait(red_full + rslot, rphase);
+                // add the eight warp partials in fixed order (every lane computes the same values), then hand
+                // the ring slot back. Both sides of this ring use the generic proxy (LDS here, STS in the
+                // consumers), whose accesses the SM orders as issued, so releasing after the reads is enough.
+                const float* sb = red_buf + rslot * kWarps * kRedStride;
+                float part[Op::K];
+#pragma unroll
+                for (int k = 0; k < Op::K; ++k) {               // same order as block_sum: warp 0, 1, ... 7
+                    float a = sb[k];
+#pragma unroll
+                    for (int w = 1; w < kWarps; ++w) a += sb[w * kRedStride + k];
+                    part[k] = a;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_empty + rslot);
+                if (++rslot == kRedSlots) { rslot = 0; rphase ^= 1u; }
+                reducer_segment<Op>(p, s, ws, row, seg.begin > 0, part);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers (warps 0..7)
     int stage = 0;
     uint32_t phase = 0;
-    const int lane = threadIdx.x & 31;
+    int rslot = 0;
+    uint32_t rphase = 0;
     for (long long row = u0 / s.upr; row * s.upr < u1; ++row) {
         const RowSeg seg = row_segment(s, u0, u1, row);
         const typename Op::Row r = Op::row_begin(p, row);
@@ -224,8 +280,8 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
                     in[i][0] = lds128(base);
                     if (Op::ub(i) == 32) in[i][1] = lds128(base + 16);
                 }
+                Op::unit(p, r, in, row * s.upr + u, acc);
             }
-            if (ok) Op::unit(p, r, in, row * s.upr + u, acc);
             // Release the stage only AFTER the unit's math and global stores: those truly depend on the
             // registers the LDS above fill, so the shared-memory reads have completed by now. Releasing
             // right after *issuing* the LDS raced with the producer's next bulk copy (async proxy) under
@@ -241,9 +297,19 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
             if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         if constexpr (Op::K > 0) {
-            double tot[Op::K];
-            if (consumer_row_reduce<Op::K>(acc, tot, s, ws, row, seg.begin > 0, red, &flag) && threadIdx.x == 0)
-                Op::row_end(p, r, row, tot);
+            // hand this warp's partial sums of the segment to the reducer warp and move on
+            float v[Op::K];
+#pragma unroll
+            for (int k = 0; k < Op::K; ++k) v[k] = warp_sum(acc[k]);
+            if (lane == 0) {
+                mbar_wait(red_empty + rslot, rphase ^ 1u);
+                float* dst = red_buf + (rslot * kWarps + warp) * kRedStride;
+#pragma unroll
+                for (int k = 0; k < Op::K; ++k) dst[k] = v[k];
+                mbar_arrive(red_full + rslot);                   // release: publishes the stores above
+            }
+            __syncwarp();
+            if (++rslot == kRedSlots) { rslot = 0; rphase ^= 1u; }
         }
     }
 }
@@ -258,6 +324,18 @@ static int launch_pipe(const typename Op::Params& p, RowWorkspace ws, long long 
         configured = true;
     }
     RowSched s = make_row_sched(B, D, W, Op::kOcc);
+    // Oversubscription: `over` spans per resident CTA slot, span id == blockIdx.x, so the HARDWARE CTA scheduler
+    // balances the load (a CTA that lands on a slow SM simply lets the others take more spans) and the
+    // prologue / epilogue of one CTA overlaps with the streaming of the other CTAs resident on its SM.
+    // Spans never shorter than 4 stages.
+    static const int over = env_int("SISS_OVERSUB", 1);
+    if (over > 1) {
+        long long g = (long long)s.grid * over;
+        const long long by_size = s.U / (4LL * kThreads);
+        if (g > by_size) g = by_size;
+        if (g > kMaxSpans) g = kMaxSpans;
+        if (g > s.grid) { s.grid = (int)g; s.nspans = (int)g; }
+    }
     static const int release_all = env_int("SISS_RELEASE_ALL", 1);   // see the release note in pipe_row_kernel
     s.release_all = release_all == 1 ? 1 : 0;
     pipe_row_kernel<Op><<<s.grid, kPipeThreads, smem, st>>>(p, ws, s);
