@@ -148,3 +148,49 @@ def test_pipelined_kernels_are_deterministic_and_match_eager_at_full_size(env):
         else:
             for x, y in zip(cur, first):
                 assert torch.equal(x, y)
+
+
+def test_k3_large_batch_takes_the_ldg_path_and_matches_eager(cuda_device):
+    """B * D / W >= 4 M units selects the register-staged LDG kernel for K3 (measured faster there): check it
+    against eager on the device at B = 192 x 3x256x256 bf16 (4.7 M units)."""
+    from siss_b200 import ops
+    from siss_b200.scheduler import SissDDPMScheduler
+    dev = cuda_device
+    Bl = 192
+    g = torch.Generator(device=dev).manual_seed(5)
+    shape = (Bl, C, H, W)
+    sched = SissDDPMScheduler()
+    gamma, sigma = sched.gamma_sigma(dev)
+    x0 = (torch.rand(shape, device=dev, generator=g) * 2 - 1).bfloat16()
+    a0 = (torch.rand(shape, device=dev, generator=g) * 2 - 1).bfloat16()
+    xm = torch.randn(shape, device=dev, generator=g).bfloat16()
+    pred = torch.randn(shape, device=dev, generator=g)
+    t = torch.randint(200, 1000, (Bl,), device=dev, generator=g)
+    w_x, w_a = torch.rand(Bl, device=dev, generator=g) * 2, torch.rand(Bl, device=dev, generator=g) * 2
+    go = 1 / 64
+    gx, ga, rlx, rla = ops.wmse_fwd_bwd(pred, xm, x0, a0, t, gamma, sigma, w_x, w_a, go, go)
+    gm, sg = gamma[t].view(-1, 1, 1, 1), sigma[t].view(-1, 1, 1, 1)
+    eps_x = (xm.float() - gm * x0.float()) / sg
+    eps_a = (xm.float() - gm * a0.float()) / sg
+    g32 = torch.tensor(go, device=dev)
+    assert torch.equal(gx, (g32 * w_x).view(-1, 1, 1, 1) * (2 * (pred - eps_x)))
+    assert torch.equal(ga, (g32 * w_a).view(-1, 1, 1, 1) * (2 * (pred - eps_a)))
+    torch.testing.assert_close(rlx.double(), ((pred - eps_x).double() ** 2).sum(dim=[1, 2, 3]), rtol=2e-6, atol=0)
+    gx2, ga2, _, _ = ops.wmse_fwd_bwd(pred, xm, x0, a0, t, gamma, sigma, w_x, w_a, go, go)
+    assert torch.equal(gx, gx2) and torch.equal(ga, ga2)
+
+
+def test_ldg_kernels_pass_the_parity_suite(cuda_device):
+    """The plain-LDG variants of the row kernels (scalar path, K3 at large sizes, SISS_NO_TMA=1) are product
+    code too: re-run the kernel parity tests in a subprocess with the TMA pipeline switched off."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, SISS_NO_TMA="1")
+    cmd = [sys.executable, "-m", "pytest", str(root / "tests" / "test_kernels_gpu.py"), str(root / "tests" / "test_fuzz_gpu.py"),
+           "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=str(root))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout
