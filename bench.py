@@ -550,9 +550,14 @@ def run_siss(args):
         # timed region 2: the same K steps again with a CUDA-event bracket around every kernel launch ->
         # per-kernel durations for the roofline (each bracket costs the stream a few microseconds, which is
         # why it is kept out of region 1; bracketed durations are therefore slightly pessimistic)
+        empty_brackets = []
         for _ in range(args.steps):
             resident_step(record=True)
+            s_e, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_e.record(); e_e.record()                      # an EMPTY bracket on the same busy stream (calibration)
+            empty_brackets.append((s_e, e_e))
         barrier()
+    empty_bracket_us = 1e3 * statistics.mean(a.elapsed_time(b) for a, b in empty_brackets)
     elapsed_ms = start.elapsed_time(end)
     el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -579,6 +584,9 @@ def run_siss(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": load_traffic(dom), "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes[dom], "ms_per_launch": kernel_ms[dom], "kernels": per_kernel,
+                "empty_event_bracket_us": empty_bracket_us,
+                "bracket_note": ("per-kernel ms are CUDA-event brackets around single launches in a second timed region; an empty "
+                                 "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/"),
                 "kernel_share_of_step": sum(kernel_ms.values()) / (elapsed_ms / args.steps)}
 
     # ---------------------------------------------------------------- e2e arm (public API, host buffers)

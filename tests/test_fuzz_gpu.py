@@ -36,7 +36,13 @@ def _cases(n, seed):
     return out
 
 
-@pytest.mark.parametrize("case", _cases(28, seed=2025), ids=lambda c: f"{c[0]}-{str(c[1]).split('.')[-1]}-l{c[2]}-t{c[3]}")
+import os
+
+N_CASES = int(os.environ.get("SISS_FUZZ_CASES", "28"))       # raise for a one-off soak (e.g. 300)
+FUZZ_SEED = int(os.environ.get("SISS_FUZZ_SEED", "2025"))
+
+
+@pytest.mark.parametrize("case", _cases(N_CASES, seed=FUZZ_SEED), ids=lambda c: f"{c[0]}-{str(c[1]).split('.')[-1]}-l{c[2]}-t{c[3]}")
 def test_fuzz_siss_path_vs_oracle(case, cuda_device):
     from siss_b200 import ops
     dev = cuda_device
