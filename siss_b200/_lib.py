@@ -62,10 +62,14 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     if not LIB_PATH.exists():
-        raise SissLibraryError(
-            f"{LIB_PATH} not found. Build it with `python -m siss_b200.build` "
-            "(or __graft_entry__.build()). siss_b200 has no CPU or PyTorch fallback."
-        )
+        # Not a fallback: the only thing tried is compiling the SAME CUDA library in place (needs nvcc).
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:
+            raise SissLibraryError(
+                f"{LIB_PATH} not found and could not be built ({e}). Build it with `python -m siss_b200.build` "
+                "(or __graft_entry__.build()). siss_b200 has no CPU or PyTorch fallback.") from e
     try:
         lib = ctypes.CDLL(str(LIB_PATH))
     except OSError as e:  # pragma: no cover - depends on the environment

@@ -48,13 +48,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cmd = [nvcc, *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB_PATH), *srcs]
+    # build next to the target and rename: atomic, so concurrent builders (one per rank under torchrun)
+    # can only ever duplicate work, never expose a half-written library
+    tmp = LIB_PATH.with_name(f"{LIB_PATH.name}.tmp.{os.getpid()}")
+    cmd += ["-o", str(tmp), *srcs]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
+        try:
+            tmp.unlink()
+        except OSError:
+            pass
         raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
     if verbose:
         sys.stderr.write(proc.stderr)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
