@@ -343,6 +343,55 @@ def load_traffic(kernel):
     return None
 
 
+def eager_gpu_reference(args, dev):
+    """EXTRA baseline: the reference's algorithm — the oracle's literal port of its loop, i.e.
+    the ~45 stock ATen launches per loss call, the per-parameter clone / subtract / norm loops and the ~20
+    `.item()` syncs — executed by eager PyTorch ON THE SAME B200 with the same stub UNet and resident inputs.
+    This is a baseline measurement only; nothing in siss_b200/ uses the oracle."""
+    from oracle import siss_oracle as O
+    dt = torch_dtype(args.dtype)
+    B = args.batch
+    shape = (B, args.channels, args.res, args.res)
+    x0_h, a0_h = synth_images(shape, dt, seed=42)
+    x0, a0 = x0_h.to(dev), a0_h.to(dev)
+    ac = O.make_alphas_cumprod()
+    gamma, sigma = O.gamma_sigma(ac)
+    gamma, sigma = gamma.to(dev), sigma.to(dev)                    # delete_celeb.py:367-371
+    loss = O.OracleDeletionLoss(gamma, sigma)
+    unet = BenchUNet(args.params).to(dev)
+    loop = O.ReferenceGradLoop(unet, train_batch_size=B, grad_accum_steps=1)
+    torch.manual_seed(42)
+
+    def step():
+        noise = torch.randn(shape, dtype=dt, device=dev)
+        t = torch.randint(999, 1000, (B,), device=dev).long()
+        all_d = {"og_latents": x0, "noisy_latents": O.add_noise(ac, x0, noise, t)}
+        del_d = {"og_latents": a0, "noisy_latents": O.add_noise(ac, a0, noise, t)}
+        items = loss.importance_sampling_with_mixture(unet, t, noise, {}, all_d, del_d, lambd=0.5)
+        O.batch_stats(items)
+        loop.micro_step(items, retain_graph=True)
+        loop.sync_step(False, scaling_norm=500.0, max_norm=1.0)
+        for p in unet.parameters():
+            p.grad = None
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    K = 10
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for _ in range(K):
+        step()
+    e_ev.record()
+    torch.cuda.synchronize()
+    ms = s_ev.elapsed_time(e_ev) / K
+    del unet, loop
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "note": ("EXTRA: the reference algorithm in stock eager PyTorch on this B200 (oracle port of the loop, inputs "
+                     "resident, same stub UNet as the e2e arm); compare with e2e.ms_per_step minus the H2D copy")}
+
+
 def extra_configs(dev):
     """BASELINE.json's other configs (parity-test cases, not bench lines): resident hot-path step of each,
     captured as ONE CUDA graph per optimiser step (these shapes are launch-bound). Supplementary numbers only."""
@@ -665,9 +714,14 @@ def run_siss(args):
         except Exception as e:  # supplementary: never break the bench line
             unlearn = {"error": repr(e)}
     others = None
+    eager_ref = None
     if rank == 0 and n == 1 and not args.no_extra_configs:
         torch.cuda.empty_cache()
         others = extra_configs(dev)
+        try:
+            eager_ref = eager_gpu_reference(args, dev)
+        except Exception as e:  # supplementary: never break the bench line
+            eager_ref = {"error": repr(e)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -675,6 +729,7 @@ def run_siss(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(), "unlearn_steps": unlearn, "other_configs": others,
+            "eager_gpu_reference": eager_ref,
         }
         emit(line)
     if world > 1:
