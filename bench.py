@@ -392,6 +392,50 @@ def eager_gpu_reference(args, dev):
                      "resident, same stub UNet as the e2e arm); compare with e2e.ms_per_step minus the H2D copy")}
 
 
+def drop_in_api_step(args, dev, sched):
+    """Supplementary: the DROP-IN path — reference-style loop body with `siss_b200.losses.DDPMDeletionLoss`
+    (materialised 7-tuple, autograd Functions), `.sum() / B` + two backward passes and `GradCombiner.combine`,
+    same stub UNet, inputs resident. The reference's statistics block is left out (it is torch code either way)."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.losses import DDPMDeletionLoss
+    dt = torch_dtype(args.dtype)
+    B = args.batch
+    shape = (B, args.channels, args.res, args.res)
+    x0_h, a0_h = synth_images(shape, dt, seed=42)
+    x0, a0 = x0_h.to(dev), a0_h.to(dev)
+    gamma, sigma = sched.gamma_sigma(dev)
+    loss_fn = DDPMDeletionLoss(gamma=gamma, sigma=sigma).importance_sampling_with_mixture
+    unet = BenchUNet(args.params).to(dev)
+    comb = GradCombiner(unet.parameters(), distributed=False)
+    keep = torch.rand(B, generator=torch.Generator().manual_seed(7)) > 0.5
+
+    def step():
+        noise = torch.randn(shape, dtype=dt, device=dev)
+        t = torch.randint(999, 1000, (B,), device=dev).long()
+        xt_x, xt_a = sched.add_noise_pair(x0, a0, noise, t)
+        items = loss_fn(unet, t, noise, {}, {"og_latents": x0, "noisy_latents": xt_x},
+                        {"og_latents": a0, "noisy_latents": xt_a}, lambd=0.5, keep_mask=keep)
+        comb.begin_x(); (items[5].sum() / B).backward(retain_graph=True)
+        comb.begin_a(); (items[6].sum() / B).backward()
+        comb.combine(scaling_norm=500.0, max_norm=1.0)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    K = 20
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for _ in range(K):
+        step()
+    e_ev.record()
+    torch.cuda.synchronize()
+    ms = s_ev.elapsed_time(e_ev) / K
+    del unet, comb
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "note": "SUPPLEMENTARY: drop-in DDPMDeletionLoss (7-tuple materialised) + GradCombiner, inputs resident, stub UNet"}
+
+
 def extra_configs(dev):
     """BASELINE.json's other configs (parity-test cases, not bench lines): resident hot-path step of each,
     captured as ONE CUDA graph per optimiser step (these shapes are launch-bound). Supplementary numbers only."""
@@ -722,6 +766,10 @@ def run_siss(args):
             eager_ref = eager_gpu_reference(args, dev)
         except Exception as e:  # supplementary: never break the bench line
             eager_ref = {"error": repr(e)}
+        try:
+            others["drop_in_api (delete_celeb shape)"] = drop_in_api_step(args, dev, sched)
+        except Exception as e:
+            others["drop_in_api (delete_celeb shape)"] = {"error": repr(e)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
