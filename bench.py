@@ -673,13 +673,36 @@ def run_siss(args):
     peak, peak_src = load_peaks()
     per_kernel = {k: {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "gbs": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9,
                       "frac": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak} for k in kernels}
+    if n == 1:
+        # Size floor: a plain device-to-device copy that moves the SAME number of bytes as each kernel (half read, half
+        # written), under the same event bracket, L2 flushed before every copy. MEASURED_PEAKS is a large-buffer
+        # figure; at 100-200 MB per launch the launch ramp / drain is a visible share of ANY kernel's duration.
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for k in kernels:
+            half = max(alg_bytes[k] // 2 // 16 * 16, 16)
+            src = torch.zeros(half, dtype=torch.uint8, device=dev)
+            dst = torch.empty_like(src)
+            pairs = []
+            for i in range(3 + 20):
+                flush.zero_()
+                s_c, e_c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_c.record(); dst.copy_(src); e_c.record()
+                if i >= 3:
+                    pairs.append((s_c, e_c))
+            torch.cuda.synchronize()
+            per_kernel[k]["copy_same_bytes_ms"] = statistics.mean(a.elapsed_time(b) for a, b in pairs)
+            per_kernel[k]["vs_copy_same_bytes"] = per_kernel[k]["copy_same_bytes_ms"] / kernel_ms[k]
+            del src, dst
+        del flush
     dom = max(kernels, key=lambda k: kernel_ms[k])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": load_traffic(dom), "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes[dom], "ms_per_launch": kernel_ms[dom], "kernels": per_kernel,
                 "empty_event_bracket_us": empty_bracket_us,
                 "bracket_note": ("per-kernel ms are CUDA-event brackets around single launches in a second timed region; an empty "
-                                 "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/"),
+                                 "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/; "
+                                 "copy_same_bytes_ms = a plain D2D copy moving the kernel's algorithmic bytes under the same "
+                                 "bracket with L2 flushed (the floor at that size), vs_copy_same_bytes = that / kernel ms"),
                 "kernel_share_of_step": sum(kernel_ms.values()) / (elapsed_ms / args.steps)}
 
     # ---------------------------------------------------------------- e2e arm (public API, host buffers)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SISS_B200_ABI_VERSION 1
+#define SISS_B200_ABI_VERSION 2
 
 enum siss_dtype { SISS_F32 = 0, SISS_BF16 = 1, SISS_F16 = 2 };
 
@@ -241,15 +241,40 @@ int siss_mt_combine(const float* const* d_gx, const float* const* d_ga, float* c
  *   d_step (nullable)    : if given, the step count is read from this DEVICE int64 instead (and `step` is
  *                          ignored), so a captured CUDA graph stays valid across optimiser steps; advance it
  *                          on the stream with siss_counter_add before the call.
+ *   d_sched (nullable)   : DEVICE double[2] = {lr, ema_decay}; if given they replace the scalar arguments, so a
+ *                          learning-rate schedule (lr_scheduler.step(), delete_celeb.py:770) and EMA warm-up
+ *                          survive CUDA-graph replay;
+ *   ema_param (nullable) : flat fp32 shadow parameters, updated in the same pass as diffusers' EMAModel.step does
+ *                          right after the optimiser step (delete_celeb.py:776-777; cfg.ema.use_ema):
+ *                          shadow -= (1 - ema_decay) * (shadow - param_new); +8 bytes/parameter.
  * 40 bytes/parameter (5 reads + 5 writes) instead of 48 in 4 launches for K4b + AdamW + 2 memsets.
  * ---------------------------------------------------------------------------------------- */
 int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const double* sums3, int mode, float value,
                        float max_norm, int inf_guard, float* param, float* exp_avg, float* exp_avg_sq,
                        double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                       const int64_t* d_step, int zero_grads, float* grad_out, float* stats5, siss_stream_t stream);
+                       const int64_t* d_step, const double* d_sched, float* ema_param, double ema_decay,
+                       int zero_grads, float* grad_out, float* stats5, siss_stream_t stream);
 
 /* *d_counter += value, stream-ordered (one thread). For the device-side optimiser step count. */
 int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Membership-loss metric (metrics/class_membership.py:66-116): I sampled images x n_noise shared noise
+ * draws at one timestep. Expanded row r = i * n_noise + j pairs image i with noise j (:76-86); the
+ * expansion is never materialised. Both calls work on the expanded-row slice [row0, row0 + rows) — one
+ * eval batch (:101-105).
+ *   siss_membership_add_noise : xt_x[q], xt_a[q] = add_noise(x0[i] | a0[i], noise[j], timestep) (:92-93),
+ *                               x0, a0 [I, D], noise [n_noise, D], outputs [rows, D], all of `dtype`;
+ *   siss_membership_sqerr     : sum_x[q] = sum_d (pred_x[q, d] - noise[j, d])^2, sum_a likewise (:108-109);
+ *                               pred_* fp32 [rows, D] (UNet outputs), noise of `dtype`; fp32 accumulation.
+ *                               workspace: siss_row_workspace_bytes(rows) zeroed bytes.
+ * ---------------------------------------------------------------------------------------- */
+int siss_membership_add_noise(const void* x0, const void* a0, const void* noise, const float* alphas_cumprod,
+                              int T, int64_t timestep, void* xt_x, void* xt_a, int64_t row0, int64_t rows,
+                              int64_t n_noise, int64_t D, int dtype, siss_stream_t stream);
+int siss_membership_sqerr(const float* pred_x, const float* pred_a, const void* noise, int dtype, float* sum_x,
+                          float* sum_a, void* workspace, int64_t row0, int64_t rows, int64_t n_noise, int64_t D,
+                          siss_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused statistics epilogue — the per-batch logging scalars of delete_celeb.py:626-656 (mean over

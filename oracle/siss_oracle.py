@@ -343,6 +343,73 @@ def combine_from_sums_cpu(g_x: Tensor, g_a: Tensor, sums3: Tensor, mode: int, va
 
 
 # --------------------------------------------------------------------------------------------------
+# EMA of the parameters (delete_celeb.py:776-777 -> diffusers.training_utils.EMAModel, diffusers==0.27.2,
+# NOT vendored by the reference: restated from that release, parity unpinned at this third-party boundary).
+# Config keys: ema.use_ema / ema_max_decay / ema_inv_gamma / ema_power (config/train_tshirt_mnist.yaml:94-97).
+# --------------------------------------------------------------------------------------------------
+class OracleEMA:
+    def __init__(self, parameters, decay: float = 0.9999, min_decay: float = 0.0, update_after_step: int = 0,
+                 use_ema_warmup: bool = False, inv_gamma: float = 1.0, power: float = 2.0 / 3.0):
+        self.shadow_params = [p.clone().detach() for p in parameters]
+        self.decay, self.min_decay, self.update_after_step = decay, min_decay, update_after_step
+        self.use_ema_warmup, self.inv_gamma, self.power = use_ema_warmup, inv_gamma, power
+        self.optimization_step = 0
+        self.cur_decay_value = None
+
+    def get_decay(self, optimization_step: int) -> float:
+        step = max(0, optimization_step - self.update_after_step - 1)
+        if step <= 0:
+            return 0.0
+        if self.use_ema_warmup:
+            cur = 1 - (1 + step / self.inv_gamma) ** -self.power
+        else:
+            cur = (1 + step) / (10 + step)
+        cur = min(cur, self.decay)
+        return max(cur, self.min_decay)
+
+    @torch.no_grad()
+    def step(self, parameters) -> None:
+        self.optimization_step += 1
+        decay = self.get_decay(self.optimization_step)
+        self.cur_decay_value = decay
+        one_minus_decay = 1 - decay
+        for s_param, param in zip(self.shadow_params, parameters):
+            if param.requires_grad:
+                s_param.sub_(one_minus_decay * (s_param - param))
+            else:
+                s_param.copy_(param)
+
+
+# --------------------------------------------------------------------------------------------------
+# Membership-loss metric (metrics/class_membership.py:69-128), pinned by tests/golden/membership_*.npz which were
+# produced by executing the reference class itself (tests/golden/make_golden_membership.py).
+# --------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def membership_losses(all_images: Tensor, deletion_images: Tensor, noise: Tensor, alphas_cumprod: Tensor, unet,
+                      timesteps: Sequence[int], eval_batch_size: int) -> List[List[Tensor]]:
+    n_img, n_noise = all_images.shape[0], noise.shape[0]
+    out = []
+    for timestep in timesteps:
+        # :76-86 — image i repeated over the noise draws, the noise set tiled over the images
+        all_flat = all_images.unsqueeze(1).expand(-1, n_noise, -1, -1, -1).reshape(-1, *all_images.shape[1:])
+        del_flat = deletion_images.unsqueeze(1).expand(-1, n_noise, -1, -1, -1).reshape(-1, *all_images.shape[1:])
+        noise_flat = noise.unsqueeze(0).expand(n_img, -1, -1, -1, -1).reshape(-1, *noise.shape[1:])
+        t_flat = torch.full((all_flat.shape[0],), timestep)                        # :89
+        noisy_all = add_noise(alphas_cumprod, all_flat, noise_flat, t_flat)        # :92-93
+        noisy_del = add_noise(alphas_cumprod, del_flat, noise_flat, t_flat)
+        all_l, del_l = [], []
+        for i in range(0, all_flat.shape[0], eval_batch_size):                     # :100-112
+            nz = noise_flat[i:i + eval_batch_size]
+            ts = t_flat[:nz.shape[0]]
+            p_all = unet(noisy_all[i:i + eval_batch_size], ts, return_dict=False)[0]
+            p_del = unet(noisy_del[i:i + eval_batch_size], ts, return_dict=False)[0]
+            all_l.append(torch.sum((p_all - nz) ** 2, dim=[1, 2, 3]))
+            del_l.append(torch.sum((p_del - nz) ** 2, dim=[1, 2, 3]))
+        out.append([torch.mean(torch.cat(all_l)), torch.mean(torch.cat(del_l))])   # :114-115
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # Per-batch statistics (delete_celeb.py:626-656) — consumed by the stats tests
 # --------------------------------------------------------------------------------------------------
 def batch_stats(items: Sequence[Optional[Tensor]]) -> Dict[str, float]:

@@ -14,7 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libsiss_b200.so"
 
 SISS_F32, SISS_BF16, SISS_F16 = 0, 1, 2
 SISS_COMBINE_SCALING_NORM, SISS_COMBINE_ERASEDIFF, SISS_COMBINE_NONE = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SissLibraryError(RuntimeError):
@@ -45,8 +45,10 @@ SIGNATURES = {
     "siss_mt_chunk_elems": (_I, []),
     "siss_mt_norm3": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "siss_mt_combine": (_I, [_P, _P, _P, _P, _P, _I, _L, _P, _I, _F, _F, _I, _P, _P]),
-    "siss_combine_adamw": (_I, [_P, _P, _L, _P, _I, _F, _F, _I, _P, _P, _P, _D, _D, _D, _D, _D, _L, _P, _I, _P, _P, _P]),
+    "siss_combine_adamw": (_I, [_P, _P, _L, _P, _I, _F, _F, _I, _P, _P, _P, _D, _D, _D, _D, _D, _L, _P, _P, _P, _D, _I, _P, _P, _P]),
     "siss_counter_add": (_I, [_P, _L, _P]),
+    "siss_membership_add_noise": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _L, _L, _L, _L, _I, _P]),
+    "siss_membership_sqerr": (_I, [_P, _P, _P, _I, _P, _P, _P, _L, _L, _L, _L, _P]),
     "siss_batch_stats": (_I, [_P, _P, _P, _P, _L, _L, _P, _P]),
     "siss_p2p_workspace_bytes": (_L, []),
     "siss_p2p_reduce_norm3": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _I, _P, _P]),

@@ -109,3 +109,23 @@ def adamw_kwargs(cfg: Dict[str, Any]) -> Dict[str, Any]:
     if "eps" in o:
         kw["eps"] = float(o["eps"])
     return kw
+
+
+def ema_kwargs(cfg: Dict[str, Any]) -> Optional[Dict[str, Any]]:
+    """``FusedCombineAdamW(ema=...)`` argument from the ``ema:`` block (config/train_tshirt_mnist.yaml:93-97;
+    ``use_ema: false`` in the three deletion configs, e.g. config/delete_celeb.yaml:86): None when EMA is off, else
+    the warm-up schedule the reference's trainer builds its EMAModel with (keys ema_max_decay / ema_inv_gamma /
+    ema_power)."""
+    e = cfg.get("ema")
+    if not isinstance(e, dict):
+        e = {"use_ema": cfg.get("use_ema", False)}          # delete_sd.yaml:75 keeps the flag at top level
+    if str(e.get("use_ema", False)).strip().lower() not in ("true", "1", "yes"):
+        return None
+    kw: Dict[str, Any] = {"use_ema_warmup": True}
+    if "ema_max_decay" in e:
+        kw["decay"] = float(e["ema_max_decay"])
+    if "ema_inv_gamma" in e:
+        kw["inv_gamma"] = float(e["ema_inv_gamma"])
+    if "ema_power" in e:
+        kw["power"] = float(e["ema_power"])
+    return kw

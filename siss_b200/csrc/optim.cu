@@ -9,6 +9,11 @@
 // Update rule, in torch's single-tensor op order (fp32):
 //     p *= 1 - lr*wd ; m += (1-b1) (g - m) ; v = v*b2 + (1-b2) g g
 //     p += (-lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+// Optional, same pass (+8 B/param): the EMA shadow update the reference runs right after the optimiser step
+// (`ema_model.step(unet.parameters())`, delete_celeb.py:776-777; diffusers EMAModel.step):
+//     shadow -= (1 - decay) * (shadow - p_new)
+// Optional `d_sched` = {lr, ema_decay} in DEVICE memory: learning-rate schedules (lr_scheduler.step(), :770) and
+// EMA warm-up then work under CUDA-graph replay, like the device-side step counter.
 
 #include "common.cuh"
 #include "combine_scalars.cuh"
@@ -29,6 +34,8 @@ struct AdamScalars {
     float neg_step;     // -lr / (1 - beta1^t)
     float eps;
     double lr, beta1_d, beta2_d;   // for the device-side step counter variant
+    double wd;                     // for the device-side lr variant
+    float ema_omd;                 // 1 - ema_decay
 };
 
 // Bias corrections from a step count held in DEVICE memory (so a captured CUDA graph stays valid from one
@@ -37,6 +44,18 @@ __device__ __forceinline__ void adam_bias_from_step(AdamScalars& a, long long st
     const double bc1 = 1.0 - pow(a.beta1_d, (double)step), bc2 = 1.0 - pow(a.beta2_d, (double)step);
     a.bc2_sqrt = (float)sqrt(bc2);
     a.neg_step = (float)(-(a.lr / bc1));
+}
+
+// lr / ema_decay from device memory; must run BEFORE adam_bias_from_step (neg_step uses a.lr)
+__device__ __forceinline__ void adam_sched_from_device(AdamScalars& a, const double* d_sched, long long host_step) {
+    a.lr = d_sched[0];
+    a.decay = (float)(1.0 - a.lr * a.wd);
+    a.ema_omd = (float)(1.0 - d_sched[1]);
+    adam_bias_from_step(a, host_step);
+}
+
+__device__ __forceinline__ float ema_update(float shadow, float p, float omd) {
+    return __fsub_rn(shadow, __fmul_rn(__fsub_rn(shadow, p), omd));   // s.sub_(omd * (s - p))
 }
 
 __global__ void counter_add_kernel(long long* p, long long v) { *p += v; }
@@ -49,13 +68,15 @@ __device__ __forceinline__ void adam_update(float g, float& p, float& m, float& 
     p = __fadd_rn(p, __fmul_rn(a.neg_step, __fdiv_rn(m, denom)));              // addcdiv_
 }
 
-template <bool TWO_TERM>
+template <bool TWO_TERM, bool EMA>
 __global__ void __launch_bounds__(kThreads, kOptOcc)
 combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n, long long nvec,
                      const double* __restrict__ sums3, int mode, float value, float max_norm, int inf_guard,
                      float* __restrict__ param, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                     AdamScalars as, const long long* __restrict__ d_step, int zero_grads,
+                     AdamScalars as, long long host_step, const long long* __restrict__ d_step,
+                     const double* __restrict__ d_sched, float* __restrict__ ema, int zero_grads,
                      float* __restrict__ grad_out, float* __restrict__ stats5) {
+    if (d_sched != nullptr) adam_sched_from_device(as, d_sched, host_step);   // lr / ema decay from device memory
     if (d_step != nullptr) adam_bias_from_step(as, *d_step);   // step count from device memory (graph replay)
     float s = 0.f, clip = 1.f;
     if (sums3 != nullptr) {
@@ -68,7 +89,7 @@ combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n
     const long long nchunks = (nvec + chunk - 1) / chunk;
     for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const long long base = (nchunks - 1 - c) * chunk + threadIdx.x;   // reverse of K4a's walk (L2 tail reuse)
-        uint4 rx[kOptUnroll], ra[kOptUnroll], rp[kOptUnroll], rm[kOptUnroll], rv[kOptUnroll];
+        uint4 rx[kOptUnroll], ra[kOptUnroll], rp[kOptUnroll], rm[kOptUnroll], rv[kOptUnroll], re[kOptUnroll];
         bool ok[kOptUnroll];
 #pragma unroll
         for (int j = 0; j < kOptUnroll; ++j) {
@@ -80,6 +101,7 @@ combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n
                 rp[j] = ldg_v4(param + 4 * i);
                 rm[j] = ldg_v4(exp_avg + 4 * i);
                 rv[j] = ldg_v4(exp_avg_sq + 4 * i);
+                if (EMA) re[j] = ldg_v4(ema + 4 * i);
             }
         }
 #pragma unroll
@@ -100,6 +122,13 @@ combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n
             stg_stream(param + 4 * i, VecTraits<float>::pack(p));
             stg_stream(exp_avg + 4 * i, VecTraits<float>::pack(m));
             stg_stream(exp_avg_sq + 4 * i, VecTraits<float>::pack(v));
+            if (EMA) {
+                float e[4];
+                VecTraits<float>::unpack(re[j], e);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[q] = ema_update(e[q], p[q], as.ema_omd);
+                stg_stream(ema + 4 * i, VecTraits<float>::pack(e));
+            }
             if (grad_out) stg_stream(grad_out + 4 * i, VecTraits<float>::pack(g));
             if (zero_grads) {
                 if (grad_out != gx) stg_stream(gx + 4 * i, zero4);
@@ -115,6 +144,7 @@ combine_adamw_kernel(float* __restrict__ gx, float* __restrict__ ga, long long n
             float p = param[i], m = exp_avg[i], v = exp_avg_sq[i];
             adam_update(g, p, m, v, as);
             param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+            if (EMA) ema[i] = ema_update(ema[i], p, as.ema_omd);
             if (grad_out) grad_out[i] = g;
             if (zero_grads) {
                 if (grad_out != gx) gx[i] = 0.f;
@@ -137,9 +167,10 @@ extern "C" int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t
 extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const double* sums3, int mode, float value,
                                   float max_norm, int inf_guard, float* param, float* exp_avg, float* exp_avg_sq,
                                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                                  const int64_t* d_step, int zero_grads, float* grad_out, float* stats5,
-                                  siss_stream_t stream) {
+                                  const int64_t* d_step, const double* d_sched, float* ema_param, double ema_decay,
+                                  int zero_grads, float* grad_out, float* stats5, siss_stream_t stream) {
     if (!g_x || !param || !exp_avg || !exp_avg_sq || n < 0 || (step < 1 && !d_step)) return SISS_EINVAL;
+    if (ema_param && !d_sched && !(ema_decay >= 0.0 && ema_decay <= 1.0)) return SISS_EINVAL;
     if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_NONE) return SISS_EINVAL;
     const bool two_term = (g_a != nullptr) && mode != SISS_COMBINE_NONE;
     if (mode != SISS_COMBINE_NONE && (!g_a || !sums3)) return SISS_EINVAL;
@@ -155,8 +186,12 @@ extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const doubl
     as.neg_step = (float)(-(lr / bc1));
     as.eps = (float)eps;
     as.lr = lr; as.beta1_d = beta1; as.beta2_d = beta2;
+    as.wd = weight_decay;
+    as.ema_omd = (float)(1.0 - ema_decay);
+    const long long hs = (long long)hstep;
     const long long* dstep = (const long long*)d_step;
-    bool al = aligned16(g_x) && aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(grad_out);
+    bool al = aligned16(g_x) && aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(grad_out) &&
+              aligned16(ema_param);
     if (two_term) al = al && aligned16(g_a);
     const long long nvec = al ? n / 4 : 0;
     const long long chunk = (long long)kThreads * kOptUnroll;
@@ -169,11 +204,12 @@ extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const doubl
     if (work < grid) grid = work;
     if (grid < 1) grid = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (two_term)
-        combine_adamw_kernel<true><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,
-                                                                   param, exp_avg, exp_avg_sq, as, dstep, zero_grads, grad_out, stats5);
-    else
-        combine_adamw_kernel<false><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,
-                                                                    param, exp_avg, exp_avg_sq, as, dstep, zero_grads, grad_out, stats5);
+#define SISS_LAUNCH_ADAMW(TT, EM)                                                                                         \
+    combine_adamw_kernel<TT, EM><<<(int)grid, kThreads, 0, st>>>(g_x, g_a, n, nvec, sums3, mode, value, max_norm, inf_guard,  \
+                                                                 param, exp_avg, exp_avg_sq, as, hs, dstep, d_sched,          \
+                                                                 ema_param, zero_grads, grad_out, stats5)
+    if (two_term) { if (ema_param) SISS_LAUNCH_ADAMW(true, true); else SISS_LAUNCH_ADAMW(true, false); }
+    else          { if (ema_param) SISS_LAUNCH_ADAMW(false, true); else SISS_LAUNCH_ADAMW(false, false); }
+#undef SISS_LAUNCH_ADAMW
     return (int)cudaGetLastError();
 }

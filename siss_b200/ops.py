@@ -420,6 +420,55 @@ def batch_stats(row_loss_x: Optional[torch.Tensor], row_loss_a: Optional[torch.T
 # ------------------------------------------------------------------------------------------------
 # multi-tensor K4 (per-parameter gradient tensors, no flat buffers)
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# Membership-loss metric (metrics/class_membership.py:66-116)
+# ------------------------------------------------------------------------------------------------
+def membership_add_noise(x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, timestep: int,
+                         alphas_cumprod: torch.Tensor, row0: int, rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Noisy all / deletion batches for expanded rows [row0, row0+rows) of the I x N_n grid (image r // N_n, noise
+    r % N_n) without materialising the expansion. x0, a0: [I, ...]; noise: [N_n, ...]."""
+    dev = _need_cuda(x0, a0, noise)
+    if x0.shape != a0.shape or x0.shape[1:] != noise.shape[1:] or not (x0.dtype == a0.dtype == noise.dtype):
+        raise ValueError("x0 / a0 [I, ...] and noise [N_n, ...] must share trailing shape and dtype")
+    x0, a0, noise = _c(x0), _c(a0), _c(noise)
+    I, D = _rows(x0)
+    n_noise = noise.shape[0]
+    if row0 < 0 or rows < 0 or row0 + rows > I * n_noise:
+        raise ValueError(f"rows [{row0}, {row0 + rows}) outside the {I} x {n_noise} expansion")
+    ac = _table(alphas_cumprod, dev)
+    if not 0 <= int(timestep) < ac.numel():
+        raise IndexError(f"timestep {timestep} outside the {ac.numel()}-step schedule")
+    shape = (rows,) + tuple(x0.shape[1:])
+    xt_x, xt_a = torch.empty(shape, dtype=x0.dtype, device=dev), torch.empty(shape, dtype=x0.dtype, device=dev)
+    if xt_x.numel() == 0:
+        return xt_x, xt_a
+    _lib.check(_lib.load().siss_membership_add_noise(_ptr(x0), _ptr(a0), _ptr(noise), _ptr(ac), ac.numel(), int(timestep),
+                                                     _ptr(xt_x), _ptr(xt_a), int(row0), int(rows), n_noise, D, _dt(x0),
+                                                     _stream()), "siss_membership_add_noise")
+    _count()
+    return xt_x, xt_a
+
+
+def membership_sqerr(pred_x: torch.Tensor, pred_a: torch.Tensor, noise: torch.Tensor,
+                     row0: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-row sum over C,H,W of (pred - noise[(row0 + q) % N_n])^2 for both predictions, one pass. -> 2x [rows] fp32."""
+    dev = _need_cuda(pred_x, pred_a, noise)
+    if pred_x.shape != pred_a.shape or pred_x.shape[1:] != noise.shape[1:]:
+        raise ValueError("pred_x / pred_a [rows, ...] and noise [N_n, ...] must share trailing shape")
+    pred_x, pred_a, noise = _c(pred_x.float()), _c(pred_a.float()), _c(noise)
+    rows, D = _rows(pred_x)
+    sum_x = torch.empty(rows, dtype=torch.float32, device=dev)
+    sum_a = torch.empty(rows, dtype=torch.float32, device=dev)
+    if pred_x.numel() == 0:
+        return sum_x.zero_(), sum_a.zero_()
+    ws = _row_workspace(dev, rows)
+    _lib.check(_lib.load().siss_membership_sqerr(_ptr(pred_x), _ptr(pred_a), _ptr(noise), _dt(noise), _ptr(sum_x),
+                                                 _ptr(sum_a), _ptr(ws), int(row0), rows, noise.shape[0], D, _stream()),
+               "siss_membership_sqerr")
+    _count()
+    return sum_x, sum_a
+
+
 class MultiTensorPlan:
     """Device-side pointer/size/chunk tables for ``siss_mt_norm3`` / ``siss_mt_combine`` over lists of fp32
     tensors ``accum_x[i]``, ``accum_a[i]`` (and ``out[i]``, default: write back into ``accum_x[i]``). Build

@@ -5,6 +5,10 @@
 buffers: parameters, both moments and the two gradient buffers are each read once and written once
 (``siss_combine_adamw``), the combined gradient itself never goes to HBM.
 
+Optional, same launch: the EMA shadow update the reference runs after the optimiser step
+(``ema_model.step(unet.parameters())``, delete_celeb.py:776-777, ``cfg.ema.*`` keys) and a learning rate /
+EMA decay read from device memory so schedules survive CUDA-graph replay (``lr_scheduler.step()``, :770).
+
 Parameters are moved into one flat fp32 buffer (``param.data`` become views, exactly like the gradients);
 the module keeps working unchanged. Under data parallel the exchange happens first (NCCL or the fused
 NVLink kernels of ``GradCombiner``), then every rank applies the identical update.
@@ -21,9 +25,26 @@ from ._lib import SISS_COMBINE_ERASEDIFF, SISS_COMBINE_NONE, SISS_COMBINE_SCALIN
 from .grad_combine import GradCombiner
 
 
+def ema_decay_at(optimization_step: int, decay: float = 0.9999, min_decay: float = 0.0, update_after_step: int = 0,
+                 use_ema_warmup: bool = False, inv_gamma: float = 1.0, power: float = 2.0 / 3.0) -> float:
+    """Decay factor of diffusers' ``EMAModel.get_decay`` (diffusers 0.27.2, not vendored by the reference; keys
+    ``ema_max_decay / ema_inv_gamma / ema_power`` of config/train_tshirt_mnist.yaml:94-97) for the 1-based
+    optimisation step: 0 on the first step (shadow := params), then warm-up or (1+s)/(10+s), clamped."""
+    step = max(0, int(optimization_step) - int(update_after_step) - 1)
+    if step <= 0:
+        return 0.0
+    cur = 1.0 - (1.0 + step / inv_gamma) ** -power if use_ema_warmup else (1.0 + step) / (10.0 + step)
+    return max(min(cur, decay), min_decay)
+
+
 class FusedCombineAdamW:
     def __init__(self, combiner: GradCombiner, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999),
-                 eps: float = 1e-8, weight_decay: float = 1e-2):
+                 eps: float = 1e-8, weight_decay: float = 1e-2, ema: Optional[dict] = None,
+                 device_schedule: bool = False):
+        """``ema``: None, or the keyword arguments of :func:`ema_decay_at` (``{}`` for its defaults) to keep a flat
+        shadow copy ``ema_flat`` updated inside the optimiser kernel. ``device_schedule``: keep {lr, ema_decay}
+        in a device record (``d_sched``) that the kernel reads, refreshed stream-ordered by :meth:`set_schedule`
+        — needed when step() is replayed from a CUDA graph with a changing learning rate / EMA warm-up."""
         self.combiner = combiner
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), \
             float(weight_decay)
@@ -39,11 +60,46 @@ class FusedCombineAdamW:
         # the step count also lives on the device and is advanced on the stream, so that a CUDA graph captured
         # around step() applies the right bias corrections on every replay
         self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ema_cfg = None if ema is None else dict(ema)
+        self.ema_flat = self.p_flat.clone() if ema is not None else None      # EMAModel.__init__: shadow = clone(params)
+        self.cur_ema_decay = 0.0
+        self.d_sched = None
+        if device_schedule:
+            self.d_sched = torch.zeros(2, dtype=torch.float64, device=dev)
+            self._sched_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+            self.set_schedule(lr=self.lr, ema_decay=0.0)
+
+    def set_schedule(self, lr: Optional[float] = None, ema_decay: Optional[float] = None) -> None:
+        """New learning rate and / or EMA decay for the following step() calls. With ``device_schedule`` the pair
+        is copied to the device record on the current stream (no host sync), so graph replays pick it up."""
+        if lr is not None:
+            self.lr = float(lr)
+        if ema_decay is not None:
+            self.cur_ema_decay = float(ema_decay)
+        if self.d_sched is not None:
+            # a fresh pinned source per update: the previous async copy may not have been consumed yet
+            self._sched_host = torch.tensor([self.lr, self.cur_ema_decay], dtype=torch.float64).pin_memory()
+            self.d_sched.copy_(self._sched_host, non_blocking=True)
+
+    # EMAModel.store / copy_to / restore, used around evaluation (delete_celeb.py:380-382) — not on the hot path
+    def ema_copy_to_params(self) -> None:
+        self._stored = self.p_flat.clone()
+        self.p_flat.copy_(self.ema_flat)
+
+    def ema_restore_params(self) -> None:
+        self.p_flat.copy_(self._stored)
+        self._stored = None
 
     def _launch(self, sums3: Optional[torch.Tensor], mode: int, value: float, max_norm: float, inf_guard: bool,
                 two_term: bool) -> None:
         cb = self.combiner
         self.step_count += 1
+        if self.ema_cfg is not None:
+            if self.d_sched is None:
+                self.cur_ema_decay = ema_decay_at(self.step_count, **self.ema_cfg)
+            elif not torch.cuda.is_current_stream_capturing():
+                # eager use of the device record; around graph replays the caller refreshes it with set_schedule()
+                self.set_schedule(ema_decay=ema_decay_at(self.step_count, **self.ema_cfg))
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.load().siss_counter_add(ctypes.c_void_p(self.d_step.data_ptr()), 1, stream), "siss_counter_add")
         _lib.check(_lib.load().siss_combine_adamw(
@@ -51,7 +107,10 @@ class FusedCombineAdamW:
             ctypes.c_void_p(0 if sums3 is None else sums3.data_ptr()), int(mode), float(value), float(max_norm),
             int(bool(inf_guard)), ctypes.c_void_p(self.p_flat.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
             ctypes.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
-            self.weight_decay, self.step_count, ctypes.c_void_p(self.d_step.data_ptr()), 1, ctypes.c_void_p(0),
+            self.weight_decay, self.step_count, ctypes.c_void_p(self.d_step.data_ptr()),
+            ctypes.c_void_p(0 if self.d_sched is None else self.d_sched.data_ptr()),
+            ctypes.c_void_p(0 if self.ema_flat is None else self.ema_flat.data_ptr()), float(self.cur_ema_decay),
+            1, ctypes.c_void_p(0),
             ctypes.c_void_p(cb.stats.data_ptr()), stream), "siss_combine_adamw")
         ops._count(2)
 

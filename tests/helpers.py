@@ -8,7 +8,23 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
-GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz"))
+GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz") if not p.stem.startswith("membership_"))
+MEMBERSHIP_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("membership_*.npz"))   # make_golden_membership.py
+
+
+def load_membership_golden(name: str) -> Dict[str, object]:
+    z = np.load(GOLDEN_DIR / f"{name}.npz", allow_pickle=False)
+    out = {k: torch.from_numpy(z[k]) for k in ("all_images", "deletion_images", "noise", "alphas_cumprod",
+                                               "dataset_all", "dataset_deletion", "losses", "losses_f32")}
+    out.update(timesteps=[int(t) for t in z["timesteps"]], eval_bs=int(z["eval_bs"]), seed=int(z["seed"]))
+    return out
+
+
+class MembershipStubUNet(torch.nn.Module):
+    """The stub the membership fixtures were generated with (make_golden_membership.py)."""
+
+    def forward(self, x, timesteps, return_dict=False, **kw):
+        return (x * 0.75 + 0.05 + timesteps.reshape(-1, 1, 1, 1).float() * 1e-4,)
 
 _LATENT_KEYS = ("x0", "a0", "noise", "xt_x", "xt_a")
 

@@ -117,9 +117,15 @@ def test_argument_validation_without_a_gpu():
     assert lib.siss_norm3(N, one, 16, one, one, N) == -1
     assert lib.siss_combine(one, one, one, 16, one, 3, 1.0, 1.0, 0, N, N) == -1          # bad mode
     assert lib.siss_combine(one, one, one, 16, N, 0, 1.0, 1.0, 0, N, N) == -1            # sums3 missing
-    assert lib.siss_combine_adamw(one, one, 16, one, 0, 1.0, 1.0, 0, one, one, one, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, N, 1,
-                                  N, N, N) == -1                                         # step < 1 and no device counter
+    assert lib.siss_combine_adamw(one, one, 16, one, 0, 1.0, 1.0, 0, one, one, one, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, N,
+                                  N, N, 0.0, 1, N, N, N) == -1                           # step < 1 and no device counter
+    assert lib.siss_combine_adamw(one, one, 16, one, 0, 1.0, 1.0, 0, one, one, one, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, N,
+                                  N, one, 1.5, 1, N, N, N) == -1                         # EMA decay outside [0, 1]
     assert lib.siss_counter_add(N, 1, N) == -1
+    assert lib.siss_membership_add_noise(one, one, one, one, 1000, 1000, one, one, 0, 1, 1, 16, 0, N) == -1   # t >= T
+    assert lib.siss_membership_add_noise(one, one, one, one, 1000, 5, one, one, 0, 1, 0, 16, 0, N) == -1      # n_noise < 1
+    assert lib.siss_membership_sqerr(one, one, one, 0, one, one, N, 0, 1, 1, 16, N) == -1                     # no workspace
+    assert lib.siss_membership_sqerr(one, one, one, 7, one, one, one, 0, 1, 1, 16, N) == -2                   # dtype
     assert lib.siss_batch_stats(one, one, one, one, 0, 16, one, N) == -1                 # B < 1
     arr = (ctypes.c_void_p * 8)(*[16 * (i + 1) for i in range(8)])
     assert lib.siss_p2p_reduce_norm3(arr, arr, arr, 3, 0, 16, one, one, one, 0, one, N) == -2   # world must be 2, 4 or 8

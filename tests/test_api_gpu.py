@@ -323,6 +323,78 @@ def test_fused_combine_adamw_matches_reference_loop_plus_torch_adamw(loss_fn, kw
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=3e-5, atol=3e-6)
 
 
+@pytest.mark.parametrize("device_schedule", [False, True])
+def test_fused_adamw_ema_and_lr_schedule(device_schedule, dev):
+    """§8(f)2 "(+EMA)": four optimiser steps with a decaying learning rate (lr_scheduler.step(), delete_celeb.py:770)
+    and the EMA shadow update (ema_model.step, :776-777; warm-up keys of train_tshirt_mnist.yaml:94-97) folded into
+    the optimiser kernel, vs reference loop + torch.optim.AdamW + LambdaLR + the oracle's EMAModel restatement.
+    With device_schedule the kernel reads {lr, ema_decay} from device memory."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.optim import FusedCombineAdamW
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    B = 4
+    hp = dict(lr=3e-3, betas=(0.95, 0.999), eps=1e-8, weight_decay=1e-2)
+    ema_kw = dict(decay=0.9999, use_ema_warmup=True, inv_gamma=1.0, power=0.75)
+    lr_at = lambda it: 1.0 - 0.2 * it
+    cpu_net = TinyNet(); gpu_net = copy.deepcopy(cpu_net).to(dev)
+    sched = SissDDPMScheduler()
+    oloss = O.OracleDeletionLoss(*O.gamma_sigma(sched.alphas_cumprod))
+    loop = O.ReferenceGradLoop(cpu_net, train_batch_size=B, grad_accum_steps=1)
+    ref_opt = torch.optim.AdamW(cpu_net.parameters(), **hp)
+    ref_sched = torch.optim.lr_scheduler.LambdaLR(ref_opt, lr_at)
+    ref_ema = O.OracleEMA(cpu_net.parameters(), **ema_kw)
+    comb = GradCombiner(gpu_net.parameters())
+    opt = FusedCombineAdamW(comb, ema=ema_kw, device_schedule=device_schedule, **hp)
+    step = UnlearnStep(gpu_net, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B,
+                       lambd=0.5, scaling_norm=5.0, max_norm=1.0)
+    torch.manual_seed(77)
+    for it in range(4):
+        x0, a0 = torch.rand(B, 1, 8, 8) * 2 - 1, torch.rand(B, 1, 8, 8) * 2 - 1
+        noise, t = torch.randn(B, 1, 8, 8), torch.randint(300, 1000, (B,))
+        keep = torch.rand(B) > 0.5
+        all_d = {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)}
+        del_d = {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}
+        loop.micro_step(oloss.importance_sampling_with_mixture(cpu_net, t, noise, {}, all_d, del_d, lambd=0.5,
+                                                               keep_mask=keep), retain_graph=True)
+        loop.sync_step(False, "importance_sampling_with_mixture", scaling_norm=5.0, max_norm=1.0)
+        ref_opt.step(); ref_sched.step(); ref_opt.zero_grad()
+        ref_ema.step(cpu_net.parameters())
+        step.micro_step(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev), keep_mask=keep)
+        step._micro = 0
+        opt.set_schedule(lr=hp["lr"] * lr_at(it))
+        opt.step(scaling_norm=5.0, max_norm=1.0)
+        assert opt.cur_ema_decay == ref_ema.cur_decay_value
+        shadow = [opt.ema_flat[o:o + p.numel()].view_as(p) for p, o in zip(comb.params, comb.offsets)]
+        for p, q, e, f in zip(gpu_net.parameters(), cpu_net.parameters(), shadow, ref_ema.shadow_params):
+            torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=3e-5, atol=3e-6)
+            torch.testing.assert_close(e.cpu(), f, rtol=3e-5, atol=3e-6)
+    assert 0.5 < opt.cur_ema_decay < 0.7                       # 1 - (1+3)^-0.75 = 0.646: warm-up is active
+    # EMAModel.store / copy_to / restore around evaluation (delete_celeb.py:380-382)
+    before = opt.p_flat.clone()
+    opt.ema_copy_to_params(); assert torch.equal(opt.p_flat, opt.ema_flat)
+    opt.ema_restore_params(); assert torch.equal(opt.p_flat, before)
+
+
+def test_ema_shadow_update_is_bitwise_the_eager_expression(dev):
+    """The in-kernel EMA is s.sub_((1-decay) * (s - p_new)) in fp32 without contraction: with zero gradients, zero
+    weight decay and lr = 0 the parameters stay put and the shadow must equal the eager expression bit for bit."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.optim import FusedCombineAdamW
+    torch.manual_seed(5)
+    net = torch.nn.Linear(257, 33).to(dev)
+    comb = GradCombiner(net.parameters())
+    opt = FusedCombineAdamW(comb, lr=0.0, weight_decay=0.0, ema=dict(decay=0.9))
+    opt.ema_flat.normal_()
+    want = opt.ema_flat.clone()
+    for it in range(1, 4):
+        opt.step(single_term=True, max_norm=None)
+        d = (1 + (it - 1)) / (10 + (it - 1)) if it > 1 else 0.0
+        want.sub_((1 - min(d, 0.9)) * (want - opt.p_flat))
+        assert torch.equal(opt.ema_flat, want), it
+
+
 @pytest.mark.parametrize("G", [1, 2])
 def test_unlearn_step_erasediff_matches_reference_loop(G, dev):
     """EraseDiff on the fast path (dual-MSE kernel, eta-mode combine: s = -max(eta - <X,A>/||A||^2, 0),

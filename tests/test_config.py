@@ -38,3 +38,29 @@ def test_reference_configs_parse():
         assert hp["loss_fn"] == "importance_sampling_with_mixture"
         for k, v in want.items():
             assert hp[k] == v, (name, k, hp[k])
+
+
+def test_ema_decay_schedule_matches_oracle_restatement():
+    """siss_b200.optim.ema_decay_at vs the oracle's EMAModel.get_decay restatement, plus hand values."""
+    import torch
+    from oracle import siss_oracle as O
+    from siss_b200.optim import ema_decay_at
+    for kw in (dict(), dict(use_ema_warmup=True, inv_gamma=1.0, power=0.75, decay=0.9999),
+               dict(decay=0.5, min_decay=0.1, update_after_step=3)):
+        ema = O.OracleEMA([torch.zeros(1)], **kw)
+        for step in range(0, 40):
+            assert ema_decay_at(step, **kw) == ema.get_decay(step)
+    assert ema_decay_at(1) == 0.0 and ema_decay_at(2) == 2.0 / 11.0
+    assert abs(ema_decay_at(2, use_ema_warmup=True, inv_gamma=1.0, power=0.75) - (1 - 2 ** -0.75)) < 1e-15
+    assert ema_decay_at(10 ** 9, decay=0.9999) == 0.9999
+
+
+def test_ema_kwargs_from_config_keys():
+    assert C.ema_kwargs({"ema": {"use_ema": False, "ema_max_decay": 0.9999}}) is None
+    assert C.ema_kwargs({"use_ema": "False"}) is None and C.ema_kwargs({}) is None
+    kw = C.ema_kwargs({"ema": {"use_ema": True, "ema_inv_gamma": 1.0, "ema_power": 0.75, "ema_max_decay": 0.9999}})
+    assert kw == {"use_ema_warmup": True, "decay": 0.9999, "inv_gamma": 1.0, "power": 0.75}
+    if REF.is_dir():      # the reference's trainer enables it, its three deletion configs turn it off
+        assert C.ema_kwargs(C.load_config(str(REF / "train_tshirt_mnist.yaml")))["power"] == 0.75
+        for name in ("delete_tshirt", "delete_celeb", "delete_sd"):
+            assert C.ema_kwargs(C.load_config(str(REF / f"{name}.yaml"))) is None

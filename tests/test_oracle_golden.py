@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, conditioning_of, load_golden
+from helpers import (GOLDEN_CASES, MEMBERSHIP_CASES, MembershipStubUNet, conditioning_of, load_golden,
+                     load_membership_golden)
 from oracle import siss_oracle as O
 
 
@@ -188,3 +189,16 @@ def test_combine_matches_literal_loop(loss_fn, kw, G):
     torch.testing.assert_close(out["norm_a"], na, rtol=1e-5, atol=0)
     torch.testing.assert_close(out["scaling_factor"].float(), s.float(), rtol=1e-4, atol=1e-7)
     assert torch.linalg.vector_norm(got) <= 1.0 + 1e-5
+
+
+@pytest.mark.parametrize("name", MEMBERSHIP_CASES)
+def test_membership_metric_restatement_vs_reference_class(name):
+    """oracle.membership_losses vs the losses the reference's MembershipLoss returned for the stored sampled images
+    and noise (metrics/class_membership.py:69-128): same torch-CPU ops in the same order -> bit-exact."""
+    c = load_membership_golden(name)
+    got = O.membership_losses(c["all_images"], c["deletion_images"], c["noise"], c["alphas_cumprod"],
+                              MembershipStubUNet(), c["timesteps"], c["eval_bs"])
+    assert len(got) == len(c["timesteps"]) == c["losses_f32"].shape[0] and len(MEMBERSHIP_CASES) >= 2
+    for (a, d), want in zip(got, c["losses_f32"]):
+        assert a.dtype == torch.float32 and a.dim() == 0
+        assert a.item() == want[0].item() and d.item() == want[1].item()
