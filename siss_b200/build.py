@@ -14,7 +14,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libsiss_b200.so"
-SOURCES = ["rowwise.cu", "wmse.cu", "combine.cu", "p2p.cu", "stats.cu", "optim.cu", "multitensor.cu", "membership.cu"]
+SOURCES = ["rowwise.cu", "wmse.cu", "combine.cu", "p2p.cu", "stats.cu", "optim.cu", "multitensor.cu", "membership.cu", "rng.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -8,6 +8,7 @@
 
 #include "bulkpipe.cuh"
 #include "noise.cuh"
+#include "philox.cuh"
 
 #include <cstdlib>
 
@@ -176,7 +177,7 @@ __device__ __forceinline__ void finalize_row_weights(double sx, double sa, doubl
     w_a[row] = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(one_m_lam, r_xa), lam));
 }
 
-template <typename T, int W, bool FUSED_NOISE>
+template <typename T, int W, bool FUSED_NOISE, bool RNG>
 __global__ void __launch_bounds__(kThreads, kK2Occ)
 mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      FUSED: unused
                const T* __restrict__ src_a,   // !FUSED: noisy forget batch    FUSED: unused
@@ -188,7 +189,9 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
                float lam, float one_m_lam,
                T* __restrict__ x_mix, float* __restrict__ dist_x, float* __restrict__ dist_a,
                float* __restrict__ w_x, float* __restrict__ w_a,
+               RngStream rng, unsigned long long elem_offset, T* __restrict__ noise_out,   // RNG only
                RowWorkspace ws, RowSched s) {
+    static_assert(!RNG || FUSED_NOISE, "in-kernel noise only makes sense fused with add_noise");
     constexpr int VPT = kK2Vpt;
     __shared__ float red[3 * kWarps];
     __shared__ int flag;
@@ -218,7 +221,7 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
                 if (e[j] >= 0) {
                     fetch_raw<T, W>(x0 + e[j], rx[j]);
                     fetch_raw<T, W>(a0 + e[j], ra[j]);
-                    fetch_raw<T, W>(third + e[j], rs[j]);
+                    if (!RNG) fetch_raw<T, W>(third + e[j], rs[j]);
                 }
             }
 #pragma unroll
@@ -227,7 +230,16 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
                 float x[W], a[W], v[W], m[W];
                 decode_raw<T, W>(rx[j], x);
                 decode_raw<T, W>(ra[j], a);
-                decode_raw<T, W>(rs[j], v);
+                if constexpr (RNG) {
+                    // eps of this unit from the counter-based stream, rounded to the latent dtype exactly as a
+                    // materialised noise tensor would hold it (siss_randn), optionally written out
+                    rng_normals<W>(rng, elem_offset + (unsigned long long)e[j], v);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) v[q] = VecTraits<T>::round(v[q]);
+                    if (noise_out) store_unit<T, W>(noise_out + e[j], v);
+                } else {
+                    decode_raw<T, W>(rs[j], v);
+                }
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
                     m[q] = FUSED_NOISE ? noised<T>(sa, s1, k ? x[q] : a[q], v[q]) : v[q];
@@ -248,10 +260,11 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
 }
 
 // TMA-pipelined K2 / K1oK2 (vector path): see bulkpipe.cuh.
-template <typename T, bool FUSED_NOISE>
+template <typename T, bool FUSED_NOISE, bool RNG = false>
 struct MixtureOp {
+    static_assert(!RNG || FUSED_NOISE, "in-kernel noise only makes sense fused with add_noise");
     static constexpr int W = VecTraits<T>::N;
-    static constexpr int NIN = 3;
+    static constexpr int NIN = RNG ? 2 : 3;   // RNG: eps is generated in registers, only x0 and a0 are streamed
     static constexpr int K = 3;
     static constexpr int kOcc = 3;
     static constexpr int kStages = 6;   // 6 x 12 KB = 72 KB per CTA, 3 CTAs/SM
@@ -261,6 +274,7 @@ struct MixtureOp {
         const uint8_t* keep; const int64_t* ts; const float* ac; const float* gamma; const float* sigma;
         int T_steps; float lam, one_m_lam;
         T* x_mix; float* dist_x; float* dist_a; float* w_x; float* w_a;
+        RngStream rng; unsigned long long elem_offset; T* noise_out;   // RNG only
     };
     struct Row { int t; bool k; float g, sa, s1; };
     __device__ static __forceinline__ Row row_begin(const Params& p, long long row) {
@@ -283,8 +297,16 @@ struct MixtureOp {
         VecTraits<T>::unpack(in[0][0], x);
         VecTraits<T>::unpack(in[1][0], a);
         // x_t of the selected source (packed 16-bit arithmetic, no conversions), or the given noisy row
-        const uint4 mraw = FUSED_NOISE ? VecTraits<T>::noised_unit(r.sa, r.s1, r.k ? in[0][0] : in[1][0], in[2][0])
-                                       : in[2][0];
+        uint4 third;
+        if constexpr (RNG) {
+            float z[W];
+            rng_normals<W>(p.rng, p.elem_offset + (unsigned long long)unit_index * W, z);
+            third = VecTraits<T>::pack(z);     // eps rounded to the latent dtype, as siss_randn stores it
+            if (p.noise_out) stg_stream(p.noise_out + unit_index * W, third);
+        } else {
+            third = in[NIN - 1][0];
+        }
+        const uint4 mraw = FUSED_NOISE ? VecTraits<T>::noised_unit(r.sa, r.s1, r.k ? in[0][0] : in[1][0], third) : third;
         VecTraits<T>::unpack(mraw, m);
 #pragma unroll
         for (int q = 0; q < W; ++q) {
@@ -302,35 +324,39 @@ struct MixtureOp {
     }
 };
 
-template <typename T, bool FUSED>
+template <typename T, bool FUSED, bool RNG = false>
 static int launch_mixture(const void* src_x, const void* src_a, const void* x0, const void* a0,
                           const void* noise, const uint8_t* keep, const int64_t* ts, const float* ac,
                           const float* gamma, const float* sigma, int T_steps, double lambd,
                           void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
-                          void* workspace, long long B, long long D, cudaStream_t st) {
+                          void* workspace, long long B, long long D, cudaStream_t st,
+                          RngStream rng = RngStream{0, 0, 0, 0}, unsigned long long elem_offset = 0,
+                          void* noise_out = nullptr) {
     constexpr int N = VecTraits<T>::N;
     // torch wraps the python scalars `lambd` and `1 - lambd` to the tensor dtype (fp32).
     const float lam = (float)lambd;
     const float one_m = (float)(1.0 - lambd);
     bool vec = (D % N == 0) && aligned16(x0) && aligned16(a0) && aligned16(x_mix);
-    vec = vec && (FUSED ? aligned16(noise) : (aligned16(src_x) && aligned16(src_a)));
+    if (RNG) vec = vec && aligned16(noise_out) && (elem_offset % 4 == 0);   // one Philox call = 4 consecutive elements
+    else vec = vec && (FUSED ? aligned16(noise) : (aligned16(src_x) && aligned16(src_a)));
     RowWorkspace ws = carve_row_workspace(workspace, B);
     if (vec && use_tma_pipeline()) {
-        using Op = MixtureOp<T, FUSED>;
+        using Op = MixtureOp<T, FUSED, RNG>;
         typename Op::Params p{(const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-                              gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a};
+                              gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a,
+                              rng, elem_offset, (T*)noise_out};
         return launch_pipe<Op>(p, ws, B, D, N, st);
     }
     if (vec) {
         RowSched s = make_row_sched(B, D, N, kK2Occ);
-        mixture_kernel<T, N, FUSED><<<s.grid, kThreads, 0, st>>>(
+        mixture_kernel<T, N, FUSED, RNG><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, s);
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, elem_offset, (T*)noise_out, ws, s);
     } else {
         RowSched s = make_row_sched(B, D, 1, kK2Occ);
-        mixture_kernel<T, 1, FUSED><<<s.grid, kThreads, 0, st>>>(
+        mixture_kernel<T, 1, FUSED, RNG><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, ws, s);
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, elem_offset, (T*)noise_out, ws, s);
     }
     return (int)cudaGetLastError();
 }
@@ -400,6 +426,21 @@ int siss_add_noise_mixture(const void* x0, const void* a0, const void* noise,
     SISS_DISPATCH_DTYPE(dtype, (launch_mixture<T, true>(nullptr, nullptr, x0, a0, noise, keep_mask, timesteps,
                                                         alphas_cumprod, gamma, sigma, T_steps, lambd, x_mix, dist_x,
                                                         dist_a, w_x, w_a, workspace, B, D, (cudaStream_t)stream)));
+}
+
+int siss_add_noise_mixture_rng(const void* x0, const void* a0, const uint8_t* keep_mask, const int64_t* timesteps,
+                               const float* alphas_cumprod, const float* gamma, const float* sigma, int T_steps,
+                               double lambd, uint64_t seed, uint64_t draw, uint64_t elem_offset,
+                               void* x_mix, void* noise_out, float* dist_x, float* dist_a, float* w_x, float* w_a,
+                               void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream) {
+    if (!x0 || !a0 || !keep_mask || !timesteps || !alphas_cumprod || !gamma || !sigma || !x_mix ||
+        !dist_x || !dist_a || !w_x || !w_a || !workspace || B < 0 || D < 1 || T_steps < 1 || (draw >> 63))
+        return SISS_EINVAL;
+    if (B == 0) return SISS_OK;
+    SISS_DISPATCH_DTYPE(dtype, (launch_mixture<T, true, true>(nullptr, nullptr, x0, a0, nullptr, keep_mask, timesteps,
+                                                              alphas_cumprod, gamma, sigma, T_steps, lambd, x_mix, dist_x,
+                                                              dist_a, w_x, w_a, workspace, B, D, (cudaStream_t)stream,
+                                                              make_rng_stream(seed, draw, false), elem_offset, noise_out)));
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ nothing here synchronises the host (the reference does ~20 ``.item()`` per micro
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -47,7 +47,12 @@ class UnlearnStep:
                  gradient_accumulation_steps: int = 1, lambd: Optional[float] = None,
                  superfactor: Optional[float] = None, scaling_norm: Optional[float] = None,
                  eta: Optional[float] = None, max_norm: Optional[float] = 1.0, inf_guard: bool = False,
-                 superfactor_decay: Optional[float] = None):
+                 superfactor_decay: Optional[float] = None, device_rng=None,
+                 t_range: Optional[Tuple[int, int]] = None):
+        """``device_rng`` (a :class:`siss_b200.rng.DeviceRng`, opt-in): draw eps, the timesteps and the Bernoulli mask
+        on the device from the counter-based stream whenever ``micro_step`` is not given them — for SISS eps is then
+        generated inside K1oK2 and never touches HBM. ``t_range`` = [lo, hi) for drawn timesteps (default: the whole
+        schedule, delete_tshirt.py:535-540; (999, 1000) reproduces delete_celeb.py:593-598)."""
         if loss_fn not in TWO_TERM + ONE_TERM:
             raise ValueError(f"unknown loss_fn {loss_fn!r}")
         if loss_fn == "importance_sampling_with_mixture" and lambd is None:
@@ -72,9 +77,12 @@ class UnlearnStep:
         self.alphas_cumprod = scheduler.alphas_cumprod.to(dev)
         self.gamma, self.sigma = scheduler.gamma_sigma(dev)
         self._micro = 0
+        self.device_rng = device_rng
+        self.t_range = (0, int(self.gamma.numel())) if t_range is None else (int(t_range[0]), int(t_range[1]))
 
     # ------------------------------------------------------------------------------------------
-    def micro_step(self, x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
+    def micro_step(self, x0: torch.Tensor, a0: torch.Tensor, noise: Optional[torch.Tensor] = None,
+                   timesteps: Optional[torch.Tensor] = None,
                    conditioning: Optional[dict] = None, keep_mask: Optional[torch.Tensor] = None,
                    forget_target: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Forward + both backward passes for one micro-batch. Returns per-sample device tensors:
@@ -85,10 +93,30 @@ class UnlearnStep:
         out: Dict[str, torch.Tensor] = {}
         cb = self.combiner
         last = self._micro == self.G - 1          # last accumulation micro-step of this optimiser step
-        if self.loss_fn == "importance_sampling_with_mixture":
+        rng, draw = self.device_rng, None
+        siss = self.loss_fn == "importance_sampling_with_mixture"
+        if noise is None or timesteps is None:
+            if rng is None:
+                raise ValueError("noise= and timesteps= are required unless the step was built with device_rng=")
+            draw = rng.next_draw()
+            if timesteps is None or (siss and keep_mask is None):
+                ts_d, keep_d = rng.draw_rows(x0.shape[0], x0.device, t_range=self.t_range if timesteps is None else None,
+                                             lambd=self.lambd if (siss and keep_mask is None) else None, draw=draw)
+                timesteps = ts_d if timesteps is None else timesteps
+                keep_mask = keep_d if keep_d is not None else keep_mask
+            if noise is None and not siss:
+                noise = rng.randn(x0.shape, x0.dtype, x0.device, draw=draw)
+            out["timesteps"] = timesteps
+        if siss:
             keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
-            x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
-                                                              self.gamma, self.sigma, self.lambd)
+            if noise is None:     # eps generated inside K1oK2 (registers only)
+                per_row = x0.numel() // max(x0.shape[0], 1)
+                x_mix, d_x, d_a, w_x, w_a, _ = ops.add_noise_mixture_rng(
+                    x0, a0, keep, timesteps, self.alphas_cumprod, self.gamma, self.sigma, self.lambd, rng.seed, draw,
+                    elem_offset=rng.row_offset * per_row)
+            else:
+                x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
+                                                                  self.gamma, self.sigma, self.lambd)
             pred = self.unet(x_mix, timesteps, **cond, return_dict=False)[0]
             g_x, g_a, rl_x, rl_a = ops.wmse_fwd_bwd(pred.detach(), x_mix, x0, a0, timesteps, self.gamma, self.sigma,
                                                     w_x, w_a, self.go, self.go)

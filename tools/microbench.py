@@ -51,6 +51,8 @@ def main():
     ac = sched.alphas_cumprod.to(dev)
     gamma, sigma = sched.gamma_sigma(dev)
     rows = []
+    from siss_b200.rng import DeviceRng
+    rng = DeviceRng(seed=42)
 
     def emit(**kw):
         kw["frac_of_peak"] = kw["gbs"] / peak
@@ -90,6 +92,12 @@ def main():
                     "siss_add_noise_pair": (5 * s_in, [lambda z=z: ops.add_noise_pair(z["x0"], z["a0"], z["nz"], z["t"], ac) for z in sets]),
                     "siss_mixture_weights": (4 * s_in, [lambda z=z: ops.mixture_weights(z["xt_x"], z["xt_a"], z["x0"], z["a0"], z["keep"], z["t"], gamma, sigma, 0.5) for z in sets]),
                     "siss_add_noise_mixture": (4 * s_in, [lambda z=z: ops.add_noise_mixture(z["x0"], z["a0"], z["nz"], z["keep"], z["t"], ac, gamma, sigma, 0.5) for z in sets]),
+                    # opt-in device RNG: eps generated in K1oK2's registers vs drawn by a separate
+                    # launch and read back; torch.randn + K1oK2 is what the default path costs for the same work
+                    "siss_add_noise_mixture_rng": (3 * s_in, [lambda z=z: ops.add_noise_mixture_rng(z["x0"], z["a0"], z["keep"], z["t"], ac, gamma, sigma, 0.5, 42, 7) for z in sets]),
+                    "siss_randn": (s_in, [lambda z=z: rng.randn(z["nz"].shape, dt, dev, draw=7) for z in sets]),
+                    "torch.randn": (s_in, [lambda z=z: torch.randn(z["nz"].shape, dtype=dt, device=dev) for z in sets]),
+                    "torch.randn+siss_add_noise_mixture": (5 * s_in, [lambda z=z: ops.add_noise_mixture(z["x0"], z["a0"], torch.randn(z["nz"].shape, dtype=dt, device=dev), z["keep"], z["t"], ac, gamma, sigma, 0.5) for z in sets]),
                     "siss_wmse_fwd_bwd": (12 + 3 * s_in, [lambda z=z: ops.wmse_fwd_bwd(z["pred"], z["x_mix"], z["x0"], z["a0"], z["t"], gamma, sigma, z["w_x"], z["w_a"], 1 / 64, 1 / 64) for z in sets]),
                     "siss_wmse_fwd(api-compat)": (20 + 3 * s_in, [lambda z=z: ops.wmse_fwd(z["pred"], z["x_mix"], z["x0"], z["a0"], z["t"], gamma, sigma, z["w_x"], z["w_a"]) for z in sets]),
                     "siss_dual_mse_fwd_bwd": (16 + s_in, [lambda z=z: ops.dual_mse_fwd_bwd(z["pred"], z["pred"], z["nz"], z["nz"], 1 / 64, 1 / 64) for z in sets]),
