@@ -756,7 +756,41 @@ def run_siss(args):
             dist.all_reduce(el2, op=dist.ReduceOp.MAX)
         e2e_ms = float(el2.item())
         assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics: {host_out}"
-        e2e = {"value": B * n * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+        # supplementary: the same loop with the opt-in device RNG (eps generated inside K1oK2, t and the Bernoulli mask
+        # drawn on the device: no torch.randn / randint launches, no CPU mask + H2D)
+        from siss_b200.rng import DeviceRng
+        step_rng = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B * n,
+                               lambd=lambd, scaling_norm=scaling_norm, max_norm=max_norm,
+                               device_rng=DeviceRng(seed=42, row_offset=rank * B), t_range=(999, 1000))
+
+        def e2e_step_rng():
+            x0, a0 = feeder.next()
+            feeder.submit([x0_p, a0_p])
+            out = step_rng.micro_step(x0, a0)
+            bs = batch_stats(out, D)
+            st = step_rng.sync_step()
+            host_out[:5].copy_(st, non_blocking=True)
+            host_out[5:].copy_(bs, non_blocking=True)
+            done.record()
+            done.synchronize()
+
+        for _ in range(3):
+            e2e_step_rng()
+        barrier()
+        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s3.record()
+        for _ in range(args.steps):
+            e2e_step_rng()
+        e3.record()
+        barrier()
+        el3 = torch.tensor([s3.elapsed_time(e3)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el3, op=dist.ReduceOp.MAX)
+        rng_ms = float(el3.item())
+        assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics (device rng): {host_out}"
+        e2e_rng = {"value": B * n * args.steps / (rng_ms / 1e3), "ms_per_step": rng_ms / args.steps,
+                   "note": "SUPPLEMENTARY: same e2e loop with UnlearnStep(device_rng=DeviceRng(...)) — opt-in seed semantics"}
+        e2e = {"value": B * n * args.steps / (e2e_ms / 1e3), "unit": UNIT, "device_rng_variant": e2e_rng,
                "h2d_bytes_per_step": int(2 * B * D * s_in + B), "d2h_bytes_per_step": int(host_out.numel() * 4),
                "ms_per_step": e2e_ms / args.steps,
                "api": "siss_b200.feed.DeviceFeeder (pinned H2D, double-buffered) + step.UnlearnStep.micro_step + "
