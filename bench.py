@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--no-copy-floor", action="store_true", help="skip the same-bytes D2D copy floor (keeps ncu launch lists clean)")
     ap.add_argument("--cpu-steps", type=int, default=16)
     ap.add_argument("--transport", choices=["auto", "p2p", "nccl"], default="auto",
                     help="N>1 gradient exchange: fused NVLink peer-memory kernels or NCCL collectives")
@@ -673,7 +674,7 @@ def run_siss(args):
     peak, peak_src = load_peaks()
     per_kernel = {k: {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "gbs": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9,
                       "frac": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak} for k in kernels}
-    if n == 1:
+    if n == 1 and not args.no_copy_floor:
         # Size floor: a plain device-to-device copy that moves the SAME number of bytes as each kernel (half read, half
         # written), under the same event bracket, L2 flushed before every copy. MEASURED_PEAKS is a large-buffer
         # figure; at 100-200 MB per launch the launch ramp / drain is a visible share of ANY kernel's duration.

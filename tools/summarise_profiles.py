@@ -29,13 +29,16 @@ for r in rows[1:]:
     a[0] += 1; a[1] += v
 tot = sum(v[1] for v in agg.values())
 lines = [f"# ncu launch list, {tag}. Command: ncu --metrics gpu__time_duration.sum --clock-control none --csv "
-         "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e",
+         "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extra-configs --no-copy-floor",
          "# Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's, not absolutes.",
          f"# {sum(v[0] for v in agg.values())} launches, {tot / 1e3:.1f} us total device time "
          "(6 resident steps = 3 warm-up + 3 timed; torch fill/randn kernels are input setup)",
-         "kernel,launches,total_us,avg_us,share"]
+         "# share_of_siss = share among this repo's kernels only (the step itself; at:: kernels are input setup)",
+         "kernel,launches,total_us,avg_us,share,share_of_siss"]
+tot_siss = sum(v[1] for k, v in agg.items() if "siss::" in k) or 1.0
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    lines.append(f"\"{name[:110]}\",{c},{t / 1e3:.2f},{t / 1e3 / c:.2f},{t / tot:.4f}")
+    own = f"{t / tot_siss:.4f}" if "siss::" in name else ""
+    lines.append(f"\"{name[:110]}\",{c},{t / 1e3:.2f},{t / 1e3 / c:.2f},{t / tot:.4f},{own}")
 (out / f"{tag}_launches_summary.csv").write_text("\n".join(lines) + "\n")
 (out / f"{tag}_launches.csv").write_text((go / f"launches_{tag}.csv").read_text())
 
