@@ -7,6 +7,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from siss_b200 import _lib, ops
+from siss_b200.rng import DeviceRng
 from siss_b200.scheduler import SissDDPMScheduler
 
 dev = torch.device("cuda", 0)
@@ -28,6 +29,15 @@ for dt in (torch.bfloat16, torch.float32):
         l, s = ops.sqerr_fwd(pred, nz, alpha=-1.5)
         ops.sqerr_bwd(pred, nz, go_loss=torch.ones_like(l))
         ops.batch_stats(m[1], m[2], m[3], m[4], shape[1] * shape[2] * shape[3])
+        # opt-in device RNG: randn, per-row draws, eps generated inside K1oK2 (TMA ring with 2 streams / LDG / scalar path)
+        rng = DeviceRng(seed=3, row_offset=1)
+        rng.randn(shape, dt, dev, draw=2)
+        rng.draw_rows(B, dev, t_range=(0, 1000), lambd=0.5)
+        ops.add_noise_mixture_rng(x0, a0, keep, t, ac, gamma, sigma, 0.5, 3, 2, elem_offset=x0[0].numel(), want_noise=True)
+        ops.add_noise_mixture_rng(x0, a0, keep, t, ac, gamma, sigma, 0.5, 3, 2, elem_offset=3)          # unaligned -> scalar path
+        # membership metric: expanded-row slices of an I x N_n grid, rows split over CTAs
+        mx, ma = ops.membership_add_noise(x0, a0, nz[:2], 437, ac, 1, 2 * B - 1)
+        ops.membership_sqerr(mx.float(), ma.float(), nz[:2], 1)
 n = (1 << 20) + 3
 gx, ga = torch.randn(n, device=dev), torch.randn(n, device=dev)
 sums = ops.norm3(gx, ga)
@@ -42,5 +52,10 @@ comb = GradCombiner(net.parameters()); opt = FusedCombineAdamW(comb, lr=1e-3)
 comb.begin_x(); net(torch.randn(8, 300, device=dev)).square().mean().backward()
 comb.begin_a(); net(torch.randn(8, 300, device=dev)).square().mean().backward()
 opt.step(scaling_norm=5.0)
+opt2 = FusedCombineAdamW(comb, lr=1e-3, ema=dict(decay=0.99), device_schedule=True)       # EMA + device-side {lr, decay}
+comb.begin_x(); net(torch.randn(8, 300, device=dev)).square().mean().backward()
+opt2.step(single_term=True); opt2.set_schedule(lr=5e-4)
+comb.begin_x(); net(torch.randn(8, 300, device=dev)).square().mean().backward()
+opt2.step(single_term=True)
 torch.cuda.synchronize()
 print("sanitize probe done")
