@@ -109,6 +109,7 @@ class GradCombiner:
         # replace these two attributes with the oracle; the product has no other path.)
         self._norm3 = ops.norm3
         self._combine = ops.combine
+        self._point(self._views_x)   # start out accumulating into G_x (needed by the after_backward_* spelling)
 
     # ------------------------------------------------------------------------------------------
     def _point(self, views: List[torch.Tensor]) -> None:
@@ -143,14 +144,36 @@ class GradCombiner:
                 self._early_done.record(self._side)
             self._early_x = True
 
+    # The same protocol in the "after" spelling SURVEY.md §8b sketches for this boundary: nothing to call before the
+    # first backward of a micro-step (the combiner starts out, and is left by after_backward_a / zero_grad /
+    # combine, pointing at G_x); zero_grad() stands in for optimizer.zero_grad() (delete_celeb.py:773), which must not
+    # be called with set_to_none=True because param.grad has to stay a view of the flat buffers.
+    def after_backward_x(self, last_micro_step: bool = False) -> None:
+        """After ``backward(weighted_loss_x)``: what follows accumulates into ``G_a`` (== :meth:`begin_a`)."""
+        self.begin_a(last_micro_step=last_micro_step)
+
+    def after_backward_a(self) -> None:
+        """After ``backward(weighted_loss_a)``: the next micro-step's keep term accumulates into ``G_x`` again."""
+        self._point(self._views_x)
+
+    def zero_grad(self) -> None:
+        """After ``optimizer.step()``: clear the combined gradient (``G_a`` was cleared by :meth:`combine`)."""
+        self._dirty_x = True
+        self.begin_x()
+
     # ------------------------------------------------------------------------------------------
     def combine(self, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
-                max_norm: Optional[float] = 1.0, inf_guard: bool = False) -> torch.Tensor:
+                max_norm: Optional[float] = 1.0, inf_guard: bool = False, *, mode: Optional[str] = None,
+                value: Optional[float] = None) -> torch.Tensor:
         """Sync-step combine. Exactly one of ``scaling_norm`` (SISS / No-IS, delete_celeb.py:746) or
         ``eta`` (EraseDiff, :741-742) must be given. Leaves the result in ``param.grad`` (views of
         ``G_x``) for ``optimizer.step()`` and returns the device tensor
         ``[norm_loss_x, norm_loss_a, scaling_factor, total_norm, clip_coef]`` (the first three are the
         reference's wandb scalars, :748). ``G_a`` is cleared for the next accumulation round."""
+        if mode is not None:                  # combine(mode="scaling_norm" | "erasediff", value=...) spelling
+            if mode not in ("scaling_norm", "erasediff") or value is None or scaling_norm is not None or eta is not None:
+                raise ValueError('mode must be "scaling_norm" or "erasediff", with value= and without scaling_norm= / eta=')
+            scaling_norm, eta = (value, None) if mode == "scaling_norm" else (None, value)
         if (scaling_norm is None) == (eta is None):
             raise ValueError("give exactly one of scaling_norm= or eta=")
         mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF

@@ -323,6 +323,34 @@ def test_fused_combine_adamw_matches_reference_loop_plus_torch_adamw(loss_fn, kw
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=3e-5, atol=3e-6)
 
 
+def test_grad_combiner_after_spelling_equals_begin_spelling(dev):
+    """SURVEY §8b sketches the combine boundary as after_backward_x / after_backward_a / combine(mode, value); both
+    spellings must drive the same kernels to bit-identical gradients over 2 optimiser steps x 2 micro-steps."""
+    from siss_b200.grad_combine import GradCombiner
+    torch.manual_seed(9)
+    net_a = TinyNet().to(dev); net_b = copy.deepcopy(net_a)
+    ca, cb = GradCombiner(net_a.parameters()), GradCombiner(net_b.parameters())
+    for it in range(2):
+        for k in range(2):
+            x = torch.randn(4, 1, 8, 8, device=dev); y = torch.randn(4, 1, 8, 8, device=dev)
+            la = net_a(x, None)[0]; lb = net_b(x, None)[0]
+            ca.begin_x(); la.square().sum().backward(retain_graph=True)
+            ca.begin_a(); (la - y).square().sum().backward()
+            lb.square().sum().backward(retain_graph=True); cb.after_backward_x()
+            (lb - y).square().sum().backward(); cb.after_backward_a()
+        sa = ca.combine(scaling_norm=5.0, max_norm=1.0) if it == 0 else ca.combine(eta=0.05, max_norm=1.0)
+        sb = cb.combine(mode="scaling_norm", value=5.0) if it == 0 else cb.combine(mode="erasediff", value=0.05)
+        assert torch.equal(sa, sb) and sa[1].item() > 0
+        for p, q in zip(net_a.parameters(), net_b.parameters()):
+            assert torch.equal(p.grad, q.grad) and p.grad.abs().sum().item() > 0
+        cb.zero_grad()                                     # the begin_* flow clears lazily in begin_x()
+        assert all(q.grad.abs().sum().item() == 0 for q in net_b.parameters())
+    with pytest.raises(ValueError):
+        cb.combine(mode="scaling_norm", value=5.0, eta=0.1)
+    with pytest.raises(ValueError):
+        cb.combine(mode="plain_neg_del", value=1.0)
+
+
 @pytest.mark.parametrize("device_schedule", [False, True])
 def test_fused_adamw_ema_and_lr_schedule(device_schedule, dev):
     """§8(f)2 "(+EMA)": four optimiser steps with a decaying learning rate (lr_scheduler.step(), delete_celeb.py:770)
