@@ -264,7 +264,9 @@ int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t stream);
  * torch.randint (:593) and the CPU `torch.rand(B) > lambd` with its H2D copy
  * (losses/ddpm_deletion_loss.py:18). This is a NEW seed semantic (hence opt-in): a value depends only on
  * (seed, draw, global element / row index), so data-parallel ranks passing their global offsets draw exactly
- * the slices of the 1-rank tensors. `draw` (< 2^63) names one independent draw, e.g. the micro-step index.
+ * the slices of the 1-rank tensors. `draw` (< 2^63) names one independent draw, e.g. the micro-step index;
+ * d_draw (nullable): read the draw index from this DEVICE uint64 instead (advance it on the stream with
+ * siss_counter_add), so a captured CUDA graph draws fresh values on every replay.
  *   siss_randn      : out[i] = N(0,1) sample of global element elem_offset + i, rounded to `dtype`;
  *   siss_draw_rows  : timesteps[r] uniform in [t_lo, t_hi) and keep_mask[r] = (uniform > lambd) for global row
  *                     row_offset + r; either output may be NULL.
@@ -274,12 +276,13 @@ int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t stream);
  *                     the randn launch. noise_out (nullable) also materialises eps, for the methods whose
  *                     target is eps itself. elem_offset = global index of this rank's first element.
  * ---------------------------------------------------------------------------------------- */
-int siss_randn(void* out, int64_t n, int dtype, uint64_t seed, uint64_t draw, uint64_t elem_offset, siss_stream_t stream);
-int siss_draw_rows(int64_t* timesteps, uint8_t* keep_mask, int64_t B, uint64_t seed, uint64_t draw, uint64_t row_offset,
-                   int64_t t_lo, int64_t t_hi, double lambd, siss_stream_t stream);
+int siss_randn(void* out, int64_t n, int dtype, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
+               siss_stream_t stream);
+int siss_draw_rows(int64_t* timesteps, uint8_t* keep_mask, int64_t B, uint64_t seed, uint64_t draw, const uint64_t* d_draw,
+                   uint64_t row_offset, int64_t t_lo, int64_t t_hi, double lambd, siss_stream_t stream);
 int siss_add_noise_mixture_rng(const void* x0, const void* a0, const uint8_t* keep_mask, const int64_t* timesteps,
                                const float* alphas_cumprod, const float* gamma, const float* sigma, int T,
-                               double lambd, uint64_t seed, uint64_t draw, uint64_t elem_offset,
+                               double lambd, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
                                void* x_mix, void* noise_out, float* dist_x, float* dist_a, float* w_x, float* w_a,
                                void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream);
 

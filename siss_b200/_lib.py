@@ -48,9 +48,9 @@ SIGNATURES = {
     "siss_mt_combine": (_I, [_P, _P, _P, _P, _P, _I, _L, _P, _I, _F, _F, _I, _P, _P]),
     "siss_combine_adamw": (_I, [_P, _P, _L, _P, _I, _F, _F, _I, _P, _P, _P, _D, _D, _D, _D, _D, _L, _P, _P, _P, _D, _I, _P, _P, _P]),
     "siss_counter_add": (_I, [_P, _L, _P]),
-    "siss_randn": (_I, [_P, _L, _I, _U, _U, _U, _P]),
-    "siss_draw_rows": (_I, [_P, _P, _L, _U, _U, _U, _L, _L, _D, _P]),
-    "siss_add_noise_mixture_rng": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _D, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "siss_randn": (_I, [_P, _L, _I, _U, _U, _P, _U, _P]),
+    "siss_draw_rows": (_I, [_P, _P, _L, _U, _U, _P, _U, _L, _L, _D, _P]),
+    "siss_add_noise_mixture_rng": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _D, _U, _U, _P, _U, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
     "siss_membership_add_noise": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _L, _L, _L, _L, _I, _P]),
     "siss_membership_sqerr": (_I, [_P, _P, _P, _I, _P, _P, _P, _L, _L, _L, _L, _P]),
     "siss_batch_stats": (_I, [_P, _P, _P, _P, _L, _L, _P, _P]),

@@ -23,6 +23,16 @@ __host__ __device__ inline RngStream make_rng_stream(uint64_t seed, uint64_t dra
     return r;
 }
 
+// `draw` held in DEVICE memory (advanced on the stream with siss_counter_add): a captured CUDA graph then draws fresh
+// values on every replay, like the optimiser's device-side step counter.
+__device__ __forceinline__ void rng_draw_from_device(RngStream& s, const unsigned long long* d_draw) {
+    if (d_draw != nullptr) {
+        const unsigned long long d = *d_draw;
+        s.d0 = (uint32_t)d;
+        s.d1 = ((uint32_t)(d >> 32) & 0x7FFFFFFFu) | (s.d1 & 0x80000000u);
+    }
+}
+
 __device__ __forceinline__ void philox4x32_10(const RngStream& s, unsigned long long index, uint32_t (&w)[4]) {
     uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = s.d0, c3 = s.d1;
     uint32_t k0 = s.k0, k1 = s.k1;

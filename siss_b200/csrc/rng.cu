@@ -12,8 +12,10 @@ int cached_sm_count();
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 4)
-randn_kernel(T* __restrict__ out, long long n, long long nvec, RngStream s, unsigned long long elem_offset) {
+randn_kernel(T* __restrict__ out, long long n, long long nvec, RngStream s, const unsigned long long* __restrict__ d_draw,
+             unsigned long long elem_offset) {
     constexpr int W = VecTraits<T>::N;
+    rng_draw_from_device(s, d_draw);
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
         float z[W];
@@ -27,8 +29,10 @@ randn_kernel(T* __restrict__ out, long long n, long long nvec, RngStream s, unsi
     }
 }
 
-__global__ void draw_rows_kernel(long long B, RngStream s, unsigned long long row_offset, long long t_lo,
+__global__ void draw_rows_kernel(long long B, RngStream s, const unsigned long long* __restrict__ d_draw,
+                                 unsigned long long row_offset, long long t_lo,
                                  unsigned int t_span, float lambd, int64_t* __restrict__ ts, uint8_t* __restrict__ keep) {
+    rng_draw_from_device(s, d_draw);
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B) return;
     uint32_t w[4];
@@ -38,7 +42,8 @@ __global__ void draw_rows_kernel(long long B, RngStream s, unsigned long long ro
 }
 
 template <typename T>
-static int launch_randn(void* out, long long n, uint64_t seed, uint64_t draw, uint64_t elem_offset, cudaStream_t st) {
+static int launch_randn(void* out, long long n, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
+                        cudaStream_t st) {
     constexpr int W = VecTraits<T>::N;
     const bool vec = aligned16(out) && (elem_offset % 4 == 0);
     const long long nvec = vec ? n / W : 0;
@@ -47,7 +52,8 @@ static int launch_randn(void* out, long long n, uint64_t seed, uint64_t draw, ui
     const long long cap = (long long)cached_sm_count() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    randn_kernel<T><<<(int)grid, kThreads, 0, st>>>((T*)out, n, nvec, make_rng_stream(seed, draw, false), elem_offset);
+    randn_kernel<T><<<(int)grid, kThreads, 0, st>>>((T*)out, n, nvec, make_rng_stream(seed, draw, false),
+                                                    (const unsigned long long*)d_draw, elem_offset);
     return (int)cudaGetLastError();
 }
 
@@ -57,26 +63,28 @@ using namespace siss;
 
 extern "C" {
 
-int siss_randn(void* out, int64_t n, int dtype, uint64_t seed, uint64_t draw, uint64_t elem_offset, siss_stream_t stream) {
+int siss_randn(void* out, int64_t n, int dtype, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
+               siss_stream_t stream) {
     if (!out || n < 0 || (draw >> 63)) return SISS_EINVAL;
     if (n == 0) return SISS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-        case SISS_F32:  return launch_randn<float>(out, n, seed, draw, elem_offset, st);
-        case SISS_BF16: return launch_randn<__nv_bfloat16>(out, n, seed, draw, elem_offset, st);
-        case SISS_F16:  return launch_randn<__half>(out, n, seed, draw, elem_offset, st);
+        case SISS_F32:  return launch_randn<float>(out, n, seed, draw, d_draw, elem_offset, st);
+        case SISS_BF16: return launch_randn<__nv_bfloat16>(out, n, seed, draw, d_draw, elem_offset, st);
+        case SISS_F16:  return launch_randn<__half>(out, n, seed, draw, d_draw, elem_offset, st);
         default: return SISS_EUNSUPPORTED;
     }
 }
 
-int siss_draw_rows(int64_t* timesteps, uint8_t* keep_mask, int64_t B, uint64_t seed, uint64_t draw, uint64_t row_offset,
-                   int64_t t_lo, int64_t t_hi, double lambd, siss_stream_t stream) {
+int siss_draw_rows(int64_t* timesteps, uint8_t* keep_mask, int64_t B, uint64_t seed, uint64_t draw, const uint64_t* d_draw,
+                   uint64_t row_offset, int64_t t_lo, int64_t t_hi, double lambd, siss_stream_t stream) {
     if ((!timesteps && !keep_mask) || B < 0 || (draw >> 63)) return SISS_EINVAL;
     if (timesteps && (t_lo < 0 || t_hi <= t_lo || t_hi - t_lo > 0x7FFFFFFFLL)) return SISS_EINVAL;
     if (B == 0) return SISS_OK;
     const unsigned int span = timesteps ? (unsigned int)(t_hi - t_lo) : 1u;
     draw_rows_kernel<<<(int)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        B, make_rng_stream(seed, draw, true), row_offset, t_lo, span, (float)lambd, timesteps, keep_mask);
+        B, make_rng_stream(seed, draw, true), (const unsigned long long*)d_draw, row_offset, t_lo, span, (float)lambd,
+        timesteps, keep_mask);
     return (int)cudaGetLastError();
 }
 

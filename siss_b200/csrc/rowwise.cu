@@ -189,8 +189,10 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
                float lam, float one_m_lam,
                T* __restrict__ x_mix, float* __restrict__ dist_x, float* __restrict__ dist_a,
                float* __restrict__ w_x, float* __restrict__ w_a,
-               RngStream rng, unsigned long long elem_offset, T* __restrict__ noise_out,   // RNG only
+               RngStream rng, const unsigned long long* __restrict__ d_draw, unsigned long long elem_offset,
+               T* __restrict__ noise_out,   // RNG only
                RowWorkspace ws, RowSched s) {
+    if (RNG) rng_draw_from_device(rng, d_draw);
     static_assert(!RNG || FUSED_NOISE, "in-kernel noise only makes sense fused with add_noise");
     constexpr int VPT = kK2Vpt;
     __shared__ float red[3 * kWarps];
@@ -274,11 +276,12 @@ struct MixtureOp {
         const uint8_t* keep; const int64_t* ts; const float* ac; const float* gamma; const float* sigma;
         int T_steps; float lam, one_m_lam;
         T* x_mix; float* dist_x; float* dist_a; float* w_x; float* w_a;
-        RngStream rng; unsigned long long elem_offset; T* noise_out;   // RNG only
+        RngStream rng; const unsigned long long* d_draw; unsigned long long elem_offset; T* noise_out;   // RNG only
     };
-    struct Row { int t; bool k; float g, sa, s1; };
+    struct Row { int t; bool k; float g, sa, s1; RngStream rs; };
     __device__ static __forceinline__ Row row_begin(const Params& p, long long row) {
         Row r;
+        if constexpr (RNG) { r.rs = p.rng; rng_draw_from_device(r.rs, p.d_draw); }   // draw index may live on the device
         r.t = wrap_timestep(p.ts[row], p.T_steps);
         r.k = p.keep[row] != 0;
         r.g = p.gamma[r.t];
@@ -300,7 +303,7 @@ struct MixtureOp {
         uint4 third;
         if constexpr (RNG) {
             float z[W];
-            rng_normals<W>(p.rng, p.elem_offset + (unsigned long long)unit_index * W, z);
+            rng_normals<W>(r.rs, p.elem_offset + (unsigned long long)unit_index * W, z);
             third = VecTraits<T>::pack(z);     // eps rounded to the latent dtype, as siss_randn stores it
             if (p.noise_out) stg_stream(p.noise_out + unit_index * W, third);
         } else {
@@ -330,8 +333,8 @@ static int launch_mixture(const void* src_x, const void* src_a, const void* x0, 
                           const float* gamma, const float* sigma, int T_steps, double lambd,
                           void* x_mix, float* dist_x, float* dist_a, float* w_x, float* w_a,
                           void* workspace, long long B, long long D, cudaStream_t st,
-                          RngStream rng = RngStream{0, 0, 0, 0}, unsigned long long elem_offset = 0,
-                          void* noise_out = nullptr) {
+                          RngStream rng = RngStream{0, 0, 0, 0}, const unsigned long long* d_draw = nullptr,
+                          unsigned long long elem_offset = 0, void* noise_out = nullptr) {
     constexpr int N = VecTraits<T>::N;
     // torch wraps the python scalars `lambd` and `1 - lambd` to the tensor dtype (fp32).
     const float lam = (float)lambd;
@@ -344,19 +347,19 @@ static int launch_mixture(const void* src_x, const void* src_a, const void* x0, 
         using Op = MixtureOp<T, FUSED, RNG>;
         typename Op::Params p{(const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
                               gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a,
-                              rng, elem_offset, (T*)noise_out};
+                              rng, d_draw, elem_offset, (T*)noise_out};
         return launch_pipe<Op>(p, ws, B, D, N, st);
     }
     if (vec) {
         RowSched s = make_row_sched(B, D, N, kK2Occ);
         mixture_kernel<T, N, FUSED, RNG><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, elem_offset, (T*)noise_out, ws, s);
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, d_draw, elem_offset, (T*)noise_out, ws, s);
     } else {
         RowSched s = make_row_sched(B, D, 1, kK2Occ);
         mixture_kernel<T, 1, FUSED, RNG><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
-            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, elem_offset, (T*)noise_out, ws, s);
+            gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, d_draw, elem_offset, (T*)noise_out, ws, s);
     }
     return (int)cudaGetLastError();
 }
@@ -430,7 +433,7 @@ int siss_add_noise_mixture(const void* x0, const void* a0, const void* noise,
 
 int siss_add_noise_mixture_rng(const void* x0, const void* a0, const uint8_t* keep_mask, const int64_t* timesteps,
                                const float* alphas_cumprod, const float* gamma, const float* sigma, int T_steps,
-                               double lambd, uint64_t seed, uint64_t draw, uint64_t elem_offset,
+                               double lambd, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
                                void* x_mix, void* noise_out, float* dist_x, float* dist_a, float* w_x, float* w_a,
                                void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream) {
     if (!x0 || !a0 || !keep_mask || !timesteps || !alphas_cumprod || !gamma || !sigma || !x_mix ||
@@ -440,7 +443,8 @@ int siss_add_noise_mixture_rng(const void* x0, const void* a0, const uint8_t* ke
     SISS_DISPATCH_DTYPE(dtype, (launch_mixture<T, true, true>(nullptr, nullptr, x0, a0, nullptr, keep_mask, timesteps,
                                                               alphas_cumprod, gamma, sigma, T_steps, lambd, x_mix, dist_x,
                                                               dist_a, w_x, w_a, workspace, B, D, (cudaStream_t)stream,
-                                                              make_rng_stream(seed, draw, false), elem_offset, noise_out)));
+                                                              make_rng_stream(seed, draw, false),
+                                                              (const unsigned long long*)d_draw, elem_offset, noise_out)));
 }
 
 }  // extern "C"

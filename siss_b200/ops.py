@@ -218,7 +218,8 @@ def add_noise_mixture(x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, k
 
 def add_noise_mixture_rng(x0: torch.Tensor, a0: torch.Tensor, keep_mask: torch.Tensor, timesteps: torch.Tensor,
                           alphas_cumprod: torch.Tensor, gamma: torch.Tensor, sigma: torch.Tensor, lambd: float,
-                          seed: int, draw: int, elem_offset: int = 0, want_noise: bool = False):
+                          seed: int, draw: int, elem_offset: int = 0, want_noise: bool = False,
+                          d_draw: Optional[torch.Tensor] = None):
     """K1 o K2 with eps drawn in-kernel from the counter-based stream (opt-in, siss_b200.rng): returns
     (x_mix, dist_x, dist_a, w_x, w_a, noise-or-None). Bit-identical to ``DeviceRng.randn`` + ``add_noise_mixture``."""
     dev = _need_cuda(x0, a0, timesteps)
@@ -237,7 +238,7 @@ def add_noise_mixture_rng(x0: torch.Tensor, a0: torch.Tensor, keep_mask: torch.T
     ws = _row_workspace(dev, B)
     _lib.check(_lib.load().siss_add_noise_mixture_rng(
         _ptr(x0), _ptr(a0), _ptr(keep), _ptr(ts), _ptr(ac), _ptr(g), _ptr(s), g.numel(), float(lambd),
-        int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw), int(elem_offset), _ptr(x_mix), _ptr(noise), _ptr(small[0]),
+        int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw), _ptr(d_draw), int(elem_offset), _ptr(x_mix), _ptr(noise), _ptr(small[0]),
         _ptr(small[1]), _ptr(small[2]), _ptr(small[3]), _ptr(ws), B, D, _dt(x0), _stream()), "siss_add_noise_mixture_rng")
     _count()
     return x_mix, small[0], small[1], small[2], small[3], noise

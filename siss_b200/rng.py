@@ -22,16 +22,27 @@ from . import _lib, ops
 
 
 class DeviceRng:
-    def __init__(self, seed: int, row_offset: int = 0):
-        """``row_offset``: this rank's first global row (``parallel.shard_bounds``) — 0 on a single GPU."""
+    def __init__(self, seed: int, row_offset: int = 0, device_counter: Optional[torch.device] = None):
+        """``row_offset``: this rank's first global row (``parallel.shard_bounds``) — 0 on a single GPU.
+        ``device_counter``: a CUDA device on which to ALSO keep the draw index (``d_draw``); the kernels then read it
+        from there and :meth:`next_draw` advances it on the stream, so a CUDA graph captured around
+        ``UnlearnStep.micro_step`` draws fresh noise / timesteps / masks on every replay (the host mirror ``draw``
+        only counts calls made outside of replays)."""
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.row_offset = int(row_offset)
         self.draw = 0                      # advanced once per micro-step by next_draw()
+        self.d_draw = None if device_counter is None else torch.zeros(1, dtype=torch.int64, device=device_counter)
 
     def next_draw(self) -> int:
-        d = self.draw
+        """The draw index for this micro-step; call advance() once all of the micro-step's draws are enqueued."""
+        return self.draw
+
+    def advance(self) -> None:
         self.draw += 1
-        return d
+        if self.d_draw is not None:
+            _lib.check(_lib.load().siss_counter_add(ctypes.c_void_p(self.d_draw.data_ptr()), 1, ops._stream()),
+                       "siss_counter_add")
+            ops._count()
 
     def randn(self, shape: Sequence[int], dtype: torch.dtype, device, draw: Optional[int] = None,
               elem_offset: Optional[int] = None) -> torch.Tensor:
@@ -43,7 +54,8 @@ class DeviceRng:
         per_row = out.numel() // out.shape[0]
         off = self.row_offset * per_row if elem_offset is None else int(elem_offset)
         _lib.check(_lib.load().siss_randn(ops._ptr(out), out.numel(), ops._dt(out), self.seed,
-                                          self.draw if draw is None else int(draw), off, ops._stream()), "siss_randn")
+                                          self.draw if draw is None else int(draw),
+                                          ops._ptr(self.d_draw if draw is None else None), off, ops._stream()), "siss_randn")
         ops._count()
         return out
 
@@ -59,7 +71,8 @@ class DeviceRng:
         if B:
             lo, hi = (0, 1) if t_range is None else (int(t_range[0]), int(t_range[1]))
             _lib.check(_lib.load().siss_draw_rows(ops._ptr(ts), ops._ptr(keep), B, self.seed,
-                                                  self.draw if draw is None else int(draw), self.row_offset, lo, hi,
+                                                  self.draw if draw is None else int(draw),
+                                                  ops._ptr(self.d_draw if draw is None else None), self.row_offset, lo, hi,
                                                   0.0 if lambd is None else float(lambd), ops._stream()), "siss_draw_rows")
             ops._count()
         return ts, keep

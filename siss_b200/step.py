@@ -98,14 +98,14 @@ class UnlearnStep:
         if noise is None or timesteps is None:
             if rng is None:
                 raise ValueError("noise= and timesteps= are required unless the step was built with device_rng=")
-            draw = rng.next_draw()
+            draw = rng.next_draw()         # an explicit draw= below would bypass the device-side counter: pass None
             if timesteps is None or (siss and keep_mask is None):
                 ts_d, keep_d = rng.draw_rows(x0.shape[0], x0.device, t_range=self.t_range if timesteps is None else None,
-                                             lambd=self.lambd if (siss and keep_mask is None) else None, draw=draw)
+                                             lambd=self.lambd if (siss and keep_mask is None) else None)
                 timesteps = ts_d if timesteps is None else timesteps
                 keep_mask = keep_d if keep_d is not None else keep_mask
             if noise is None and not siss:
-                noise = rng.randn(x0.shape, x0.dtype, x0.device, draw=draw)
+                noise = rng.randn(x0.shape, x0.dtype, x0.device)
             out["timesteps"] = timesteps
         if siss:
             keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
@@ -113,7 +113,7 @@ class UnlearnStep:
                 per_row = x0.numel() // max(x0.shape[0], 1)
                 x_mix, d_x, d_a, w_x, w_a, _ = ops.add_noise_mixture_rng(
                     x0, a0, keep, timesteps, self.alphas_cumprod, self.gamma, self.sigma, self.lambd, rng.seed, draw,
-                    elem_offset=rng.row_offset * per_row)
+                    elem_offset=rng.row_offset * per_row, d_draw=rng.d_draw)
             else:
                 x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
                                                                   self.gamma, self.sigma, self.lambd)
@@ -161,6 +161,8 @@ class UnlearnStep:
             out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl
         if self.superfactor is not None and self.superfactor_decay is not None:
             self.superfactor *= self.superfactor_decay
+        if draw is not None:
+            rng.advance()                  # next micro-step draws from the next index (host mirror + device counter)
         self._micro += 1
         return out
 

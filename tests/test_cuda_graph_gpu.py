@@ -100,3 +100,58 @@ def test_optimizer_step_is_graph_capturable(cuda_device, fused_opt):
             got = torch.cat([p.detach().reshape(-1) for p in net_g.parameters()])
             torch.testing.assert_close(got, eager[i][3], rtol=1e-5, atol=1e-6)
             assert int(opt_g.d_step.item()) == i + 1
+
+
+@pytest.mark.parametrize("loss_fn", ["importance_sampling_with_mixture", "naive_del"])
+def test_device_rng_draws_fresh_values_on_every_graph_replay(cuda_device, loss_fn):
+    """Opt-in device RNG with the draw index in device memory (DeviceRng(device_counter=...)): a captured optimiser
+    step — which draws eps, t and the Bernoulli mask itself — must produce, on replay k, exactly the eager run's
+    step with draw index k (not the captured one again)."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.rng import DeviceRng
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    dev = cuda_device
+    torch.backends.cudnn.allow_tf32 = False
+    B, shape = 32, (32, 1, 28, 28)
+    g = torch.Generator(device=dev).manual_seed(3)
+    x0 = torch.rand(shape, device=dev, generator=g) * 2 - 1
+    a0 = torch.rand(shape, device=dev, generator=g) * 2 - 1
+    kw = dict(lambd=0.5, scaling_norm=5.0) if loss_fn.startswith("importance") else {}
+
+    def make(device_counter):
+        net = TinyNet().to(dev)
+        comb = GradCombiner(net.parameters())
+        step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn=loss_fn, train_batch_size=B, max_norm=1.0,
+                           device_rng=DeviceRng(seed=17, device_counter=dev if device_counter else None), **kw)
+        return net, step
+
+    def one(step):
+        out = step.micro_step(x0, a0)
+        return out["timesteps"], step.sync_step()
+
+    net_e, step_e = make(False)
+    eager = []
+    for _ in range(4):
+        ts, gs = one(step_e)
+        eager.append((ts.clone(), gs.clone(), torch.cat([p.grad.reshape(-1) for p in net_e.parameters()]).clone()))
+    assert not torch.equal(eager[0][0], eager[1][0]) and not torch.equal(eager[1][2], eager[2][2])   # draws do differ
+
+    net_g, step_g = make(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        one(step_g)                                      # draw 0, eagerly
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ts_static, gs_static = one(step_g)               # captured while the device counter reads 1
+    for k in (1, 2, 3):
+        graph.replay()
+        torch.cuda.synchronize()
+        assert int(step_g.device_rng.d_draw.item()) == k + 1
+        assert torch.equal(ts_static, eager[k][0]), k
+        torch.testing.assert_close(gs_static, eager[k][1], rtol=1e-4, atol=1e-7)
+        got = torch.cat([p.grad.reshape(-1) for p in net_g.parameters()])
+        torch.testing.assert_close(got, eager[k][2], rtol=2e-4, atol=1e-6)
