@@ -203,6 +203,24 @@ class GradCombiner:
         self._point(self._views_x)
         return self.stats
 
+    def reduce_to_shards(self, single_term: bool = False) -> torch.Tensor:
+        """Data parallel only — the first half of the exchange: reduce-scatter the gradient buffer(s) into this rank's
+        1/N shard(s) (``_shard_x`` / ``_shard_a``) and all-reduce the three global sums. Returns ``sums3`` (global).
+        The sharded (ZeRO-1) optimiser step of :class:`siss_b200.optim.FusedCombineAdamW` continues from here: it
+        updates only this rank's shard of the parameters and all-gathers PARAMETERS instead of gradients."""
+        if self.world == 1:
+            raise RuntimeError("reduce_to_shards() is a data-parallel step")
+        if self._early_x:
+            torch.cuda.current_stream(self.device).wait_event(self._early_done)
+        else:
+            dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+        if not single_term:
+            dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
+        self._norm3(self._shard_x, self._shard_x if single_term else self._shard_a, out=self.sums3)
+        dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)
+        self._early_x = False
+        return self.sums3
+
     def clip_only(self, max_norm: float = 1.0) -> torch.Tensor:
         """Single-term methods (naive_del / simple_neg_del: ``loss is not None``, delete_celeb.py:682-684):
         gradients are in ``G_x``; only the data-parallel sum and ``clip_grad_norm_`` apply."""

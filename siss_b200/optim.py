@@ -40,11 +40,15 @@ def ema_decay_at(optimization_step: int, decay: float = 0.9999, min_decay: float
 class FusedCombineAdamW:
     def __init__(self, combiner: GradCombiner, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, ema: Optional[dict] = None,
-                 device_schedule: bool = False):
+                 device_schedule: bool = False, shard_optimizer: Optional[bool] = None):
         """``ema``: None, or the keyword arguments of :func:`ema_decay_at` (``{}`` for its defaults) to keep a flat
         shadow copy ``ema_flat`` updated inside the optimiser kernel. ``device_schedule``: keep {lr, ema_decay}
         in a device record (``d_sched``) that the kernel reads, refreshed stream-ordered by :meth:`set_schedule`
-        — needed when step() is replayed from a CUDA graph with a changing learning rate / EMA warm-up."""
+        — needed when step() is replayed from a CUDA graph with a changing learning rate / EMA warm-up.
+        ``shard_optimizer`` (data parallel; default: on with the NCCL transport, off with the fused peer-memory
+        transport): ZeRO-1 layout — reduce-scatter the gradients, update only this rank's 1/N shard of parameters,
+        moments and EMA shadow, all-gather the PARAMETERS. Same bytes on NVLink as all-gathering the combined
+        gradient, but the 40 B/param optimiser pass and the optimiser state shrink by N."""
         self.combiner = combiner
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), \
             float(weight_decay)
@@ -54,14 +58,23 @@ class FusedCombineAdamW:
             view = self.p_flat[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-        self.exp_avg = torch.zeros_like(self.p_flat)
-        self.exp_avg_sq = torch.zeros_like(self.p_flat)
+        if shard_optimizer is None:
+            shard_optimizer = combiner.world > 1 and combiner.peer is None
+        self.sharded = bool(shard_optimizer) and combiner.world > 1
+        if self.sharded:
+            lo = combiner.rank * combiner.shard_len
+            self.p_shard = self.p_flat[lo:lo + combiner.shard_len]          # view: updated in place, then all-gathered
+        else:
+            self.p_shard = self.p_flat
+        self.exp_avg = torch.zeros_like(self.p_shard)
+        self.exp_avg_sq = torch.zeros_like(self.p_shard)
         self.step_count = 0
         # the step count also lives on the device and is advanced on the stream, so that a CUDA graph captured
         # around step() applies the right bias corrections on every replay
         self.d_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.ema_cfg = None if ema is None else dict(ema)
-        self.ema_flat = self.p_flat.clone() if ema is not None else None      # EMAModel.__init__: shadow = clone(params)
+        # EMAModel.__init__: shadow = clone(params). Sharded: this rank's slice only (gathered on demand).
+        self.ema_flat = self.p_shard.clone() if ema is not None else None
         self.cur_ema_decay = 0.0
         self.d_sched = None
         if device_schedule:
@@ -84,15 +97,20 @@ class FusedCombineAdamW:
     # EMAModel.store / copy_to / restore, used around evaluation (delete_celeb.py:380-382) — not on the hot path
     def ema_copy_to_params(self) -> None:
         self._stored = self.p_flat.clone()
-        self.p_flat.copy_(self.ema_flat)
+        if self.sharded:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.p_flat, self.ema_flat, group=self.combiner.group)
+        else:
+            self.p_flat.copy_(self.ema_flat)
 
     def ema_restore_params(self) -> None:
         self.p_flat.copy_(self._stored)
         self._stored = None
 
     def _launch(self, sums3: Optional[torch.Tensor], mode: int, value: float, max_norm: float, inf_guard: bool,
-                two_term: bool) -> None:
+                two_term: bool, shard: bool = False) -> None:
         cb = self.combiner
+        g_x, g_a, n = (cb._shard_x, cb._shard_a, cb.shard_len) if shard else (cb.g_x, cb.g_a, cb.total)
         self.step_count += 1
         if self.ema_cfg is not None:
             if self.d_sched is None:
@@ -103,14 +121,14 @@ class FusedCombineAdamW:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.load().siss_counter_add(ctypes.c_void_p(self.d_step.data_ptr()), 1, stream), "siss_counter_add")
         _lib.check(_lib.load().siss_combine_adamw(
-            ctypes.c_void_p(cb.g_x.data_ptr()), ctypes.c_void_p(cb.g_a.data_ptr() if two_term else 0), cb.total,
+            ctypes.c_void_p(g_x.data_ptr()), ctypes.c_void_p(g_a.data_ptr() if two_term else 0), n,
             ctypes.c_void_p(0 if sums3 is None else sums3.data_ptr()), int(mode), float(value), float(max_norm),
-            int(bool(inf_guard)), ctypes.c_void_p(self.p_flat.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
+            int(bool(inf_guard)), ctypes.c_void_p(self.p_shard.data_ptr()), ctypes.c_void_p(self.exp_avg.data_ptr()),
             ctypes.c_void_p(self.exp_avg_sq.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
             self.weight_decay, self.step_count, ctypes.c_void_p(self.d_step.data_ptr()),
             ctypes.c_void_p(0 if self.d_sched is None else self.d_sched.data_ptr()),
             ctypes.c_void_p(0 if self.ema_flat is None else self.ema_flat.data_ptr()), float(self.cur_ema_decay),
-            1, ctypes.c_void_p(0),
+            0 if shard else 1, ctypes.c_void_p(0),
             ctypes.c_void_p(cb.stats.data_ptr()), stream), "siss_combine_adamw")
         ops._count(2)
 
@@ -121,6 +139,24 @@ class FusedCombineAdamW:
         ``GradCombiner.combine``. Gradient buffers are left cleared."""
         cb = self.combiner
         mn = 0.0 if max_norm is None else float(max_norm)
+        if cb.world > 1 and self.sharded:
+            # ZeRO-1: gradients -> shards, global scalars, combine + clip + AdamW (+EMA) on the shard, parameters gathered
+            import torch.distributed as dist
+            if not single_term and (scaling_norm is None) == (eta is None):
+                raise ValueError("give exactly one of scaling_norm= or eta= (or single_term=True)")
+            sums = cb.reduce_to_shards(single_term)
+            if single_term:
+                self._launch(sums, SISS_COMBINE_NONE, 0.0, mn, False, two_term=False, shard=True)
+            else:
+                mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF
+                self._launch(sums, mode, float(scaling_norm if eta is None else eta), mn, inf_guard, two_term=True, shard=True)
+            dist.all_gather_into_tensor(self.p_flat, self.p_shard, group=cb.group)
+            cb.g_x.zero_()
+            if not single_term:
+                cb.g_a.zero_()
+            cb._dirty_x = False
+            cb._point(cb._views_x)
+            return cb.stats
         if cb.world > 1:
             # exchange + combine first (result in G_x on every rank), then the update on the combined gradient
             if single_term:

@@ -32,8 +32,9 @@ def _batch(Bg):
             torch.randn(Bg, 1, 16, 16, generator=g), torch.randint(300, 1000, (Bg,), generator=g))
 
 
-def _run_opt(rank, world, Bg, transport="auto"):
-    """Three optimiser steps with the fused combine+AdamW under data parallel; returns the final parameters."""
+def _run_opt(rank, world, Bg, transport="auto", shard=None):
+    """Three optimiser steps with the fused combine+AdamW (+EMA) under data parallel; returns the final parameters
+    followed by the EMA shadow parameters. ``shard``: ZeRO-1 optimiser sharding (None = the transport's default)."""
     from siss_b200 import parallel
     from siss_b200.grad_combine import GradCombiner
     from siss_b200.optim import FusedCombineAdamW
@@ -43,7 +44,12 @@ def _run_opt(rank, world, Bg, transport="auto"):
     dev = torch.device("cuda", rank if world > 1 else 0)
     net = TinyNet().to(dev)
     comb = GradCombiner(net.parameters(), transport=transport)
-    opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2)
+    opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, ema=dict(decay=0.9),
+                            shard_optimizer=shard)
+    if world > 1:
+        assert opt.sharded == ((transport == "nccl") if shard is None else shard)
+        if opt.sharded:
+            assert opt.exp_avg.numel() == comb.total // world and opt.ema_flat.numel() == comb.total // world
     step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
                        train_batch_size=Bg, lambd=0.5, scaling_norm=5.0, max_norm=1.0)
     torch.manual_seed(23)
@@ -54,8 +60,14 @@ def _run_opt(rank, world, Bg, transport="auto"):
         step.micro_step(sh(x0 + 0.02 * it), sh(a0), sh(noise), sh(t), keep_mask=keep)
         step._micro = 0
         opt.step(scaling_norm=5.0, max_norm=1.0)
+        assert comb.g_x.abs().max().item() == 0.0 and comb.g_a.abs().max().item() == 0.0
     torch.cuda.synchronize()
-    return torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
+    final = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
+    opt.ema_copy_to_params()                      # sharded: all-gathers the shadow shards
+    shadow = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
+    opt.ema_restore_params()
+    assert torch.equal(torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu(), final)
+    return torch.cat([final, shadow])
 
 
 def _run(rank, world, Bg, G, transport="auto"):
@@ -93,6 +105,7 @@ def _worker(rank, world, port, q):
         out[transport] = _run(rank, world, 8, 2, transport)
         if world == 2:
             out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
+            out[transport + "/fused_adamw_other_layout"] = _run_opt(rank, world, 8, transport, shard=(transport == "p2p"))
     if rank == 0:
         q.put(out)
     dist.barrier()
@@ -116,7 +129,7 @@ def test_multi_gpu_step_equals_single_gpu(world):
     flat1, stats1 = _run(0, 1, 8, 2)
     params1 = _run_opt(0, 1, 8) if world == 2 else None
     for transport, res in out.items():                  # NCCL collectives and fused NVLink peer-memory kernels
-        if transport.endswith("/fused_adamw"):
+        if "/fused_adamw" in transport:                 # replicated and ZeRO-1 sharded layouts, parameters + EMA shadow
             torch.testing.assert_close(res, params1, rtol=3e-5, atol=3e-6, msg=lambda m: f"{transport}: {m}")
             continue
         flat2, stats2 = res
