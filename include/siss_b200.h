@@ -350,6 +350,19 @@ int siss_p2p_combine_allgather(const float* shard_x, const float* shard_a, const
                                int mode, float value, float max_norm, int inf_guard, float* stats5,
                                siss_stream_t stream);
 
+/* Sharded (ZeRO-1) optimiser step fused with the PARAMETER all-gather — the data-parallel form of
+ * siss_combine_adamw (delete_celeb.py:714-773): K4b on this rank's gradient shard, the AdamW (+EMA) update of this
+ * rank's shard of parameters / moments in registers, new parameters stored to elements [rank*shard_len, ...) of
+ * every peer's flat parameter buffer h_peers_param[r] (own included). exp_avg / exp_avg_sq / ema_shard are LOCAL
+ * shard-sized buffers. Follows siss_p2p_reduce_norm3 + barrier exactly like siss_p2p_combine_allgather, and needs a
+ * barrier after it before any rank reads its parameters. step / d_step / d_sched / ema_* as in siss_combine_adamw. */
+int siss_p2p_adamw_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                             float* const* h_peers_param, int world, int rank, int64_t shard_len,
+                             int mode, float value, float max_norm, int inf_guard,
+                             float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
+                             float* ema_shard, double ema_decay, float* stats5, siss_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "combine_scalars.cuh"
+#include "adam.cuh"
 
 namespace siss {
 
@@ -25,48 +26,7 @@ int cached_sm_count();
 constexpr int kOptOcc = 3;
 constexpr int kOptUnroll = 2;
 
-struct AdamScalars {
-    float decay;        // 1 - lr * weight_decay
-    float w1;           // 1 - beta1
-    float beta2;
-    float w2;           // 1 - beta2
-    float bc2_sqrt;     // sqrt(1 - beta2^t)
-    float neg_step;     // -lr / (1 - beta1^t)
-    float eps;
-    double lr, beta1_d, beta2_d;   // for the device-side step counter variant
-    double wd;                     // for the device-side lr variant
-    float ema_omd;                 // 1 - ema_decay
-};
-
-// Bias corrections from a step count held in DEVICE memory (so a captured CUDA graph stays valid from one
-// optimiser step to the next): same double-precision expressions the host path evaluates.
-__device__ __forceinline__ void adam_bias_from_step(AdamScalars& a, long long step) {
-    const double bc1 = 1.0 - pow(a.beta1_d, (double)step), bc2 = 1.0 - pow(a.beta2_d, (double)step);
-    a.bc2_sqrt = (float)sqrt(bc2);
-    a.neg_step = (float)(-(a.lr / bc1));
-}
-
-// lr / ema_decay from device memory; must run BEFORE adam_bias_from_step (neg_step uses a.lr)
-__device__ __forceinline__ void adam_sched_from_device(AdamScalars& a, const double* d_sched, long long host_step) {
-    a.lr = d_sched[0];
-    a.decay = (float)(1.0 - a.lr * a.wd);
-    a.ema_omd = (float)(1.0 - d_sched[1]);
-    adam_bias_from_step(a, host_step);
-}
-
-__device__ __forceinline__ float ema_update(float shadow, float p, float omd) {
-    return __fsub_rn(shadow, __fmul_rn(__fsub_rn(shadow, p), omd));   // s.sub_(omd * (s - p))
-}
-
 __global__ void counter_add_kernel(long long* p, long long v) { *p += v; }
-
-__device__ __forceinline__ void adam_update(float g, float& p, float& m, float& v, const AdamScalars& a) {
-    p = __fmul_rn(p, a.decay);
-    m = __fadd_rn(m, __fmul_rn(a.w1, __fsub_rn(g, m)));                        // lerp, small weight branch
-    v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(a.w2, g), g));    // mul_ ; addcmul_
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), a.bc2_sqrt), a.eps);
-    p = __fadd_rn(p, __fmul_rn(a.neg_step, __fdiv_rn(m, denom)));              // addcdiv_
-}
 
 template <bool TWO_TERM, bool EMA>
 __global__ void __launch_bounds__(kThreads, kOptOcc)
@@ -174,21 +134,8 @@ extern "C" int siss_combine_adamw(float* g_x, float* g_a, int64_t n, const doubl
     if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_NONE) return SISS_EINVAL;
     const bool two_term = (g_a != nullptr) && mode != SISS_COMBINE_NONE;
     if (mode != SISS_COMBINE_NONE && (!g_a || !sums3)) return SISS_EINVAL;
-    // python-float scalars of torch.optim.AdamW's single-tensor path, rounded to fp32 where the tensor op does
-    AdamScalars as;
-    as.decay = (float)(1.0 - lr * weight_decay);
-    as.w1 = (float)(1.0 - beta1);
-    as.beta2 = (float)beta2;
-    as.w2 = (float)(1.0 - beta2);
-    const double hstep = (double)(step < 1 ? 1 : step);
-    const double bc1 = 1.0 - pow(beta1, hstep), bc2 = 1.0 - pow(beta2, hstep);
-    as.bc2_sqrt = (float)sqrt(bc2);
-    as.neg_step = (float)(-(lr / bc1));
-    as.eps = (float)eps;
-    as.lr = lr; as.beta1_d = beta1; as.beta2_d = beta2;
-    as.wd = weight_decay;
-    as.ema_omd = (float)(1.0 - ema_decay);
-    const long long hs = (long long)hstep;
+    long long hs;
+    const AdamScalars as = make_adam_scalars(lr, beta1, beta2, eps, weight_decay, step, ema_decay, hs);
     const long long* dstep = (const long long*)d_step;
     bool al = aligned16(g_x) && aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq) && aligned16(grad_out) &&
               aligned16(ema_param);

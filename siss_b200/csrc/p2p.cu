@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "combine_scalars.cuh"
+#include "adam.cuh"
 
 namespace siss {
 
@@ -189,6 +190,81 @@ p2p_combine_allgather_kernel(const float* __restrict__ shard_x, const float* __r
     }
 }
 
+// Sharded (ZeRO-1) optimiser step fused with the parameter all-gather: K4b on this rank's gradient shard, the
+// AdamW (+EMA) update of this rank's shard of parameters / moments in registers, and the NEW PARAMETERS stored
+// to every peer's flat parameter buffer (instead of the combined gradient to every peer's G_x). Same outbound
+// NVLink bytes as p2p_combine_allgather_kernel; the 40 B/param optimiser pass over the full buffer disappears
+// from every rank (it is done once, on 1/WORLD of the parameters, here).
+template <int WORLD, int U, bool EMA>
+__global__ void __launch_bounds__(kThreads, kP2POcc)
+p2p_adamw_allgather_kernel(const float* __restrict__ shard_x, const float* __restrict__ shard_a,
+                           const double* __restrict__ scalar_slots, int rank, long long shard_len, PeerOut peers,
+                           const float* __restrict__ p_local /* this rank's shard of its own parameter buffer */,
+                           float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ ema,
+                           AdamScalars as, long long host_step, const long long* __restrict__ d_step,
+                           const double* __restrict__ d_sched, int mode, float value, float max_norm, int inf_guard,
+                           float* __restrict__ stats5) {
+    if (d_sched != nullptr) adam_sched_from_device(as, d_sched, host_step);
+    if (d_step != nullptr) adam_bias_from_step(as, *d_step);
+    double sxx = 0.0, saa = 0.0, sxa = 0.0;
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) {   // rank order: identical on every rank
+        sxx += scalar_slots[4 * r + 0];
+        saa += scalar_slots[4 * r + 1];
+        sxa += scalar_slots[4 * r + 2];
+    }
+    const CombineScalars cs = combine_scalars_from(sxx, saa, sxa, mode, value, max_norm, inf_guard, stats5,
+                                                   blockIdx.x == 0 && threadIdx.x == 0);
+    const float s = cs.s, clip = cs.clip;
+    const long long nvec = shard_len / 4;
+    const long long base_elem = (long long)rank * shard_len;
+    const long long chunk = (long long)kThreads * U;
+    const long long nchunks = (nvec + chunk - 1) / chunk;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        uint4 rx[U], ra[U], rp[U], rm[U], rv[U], re[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = c * chunk + (long long)u * kThreads + threadIdx.x;
+            ok[u] = i < nvec;
+            if (ok[u]) {
+                rx[u] = ldg_stream(shard_x + 4 * i); ra[u] = ldg_stream(shard_a + 4 * i);
+                rp[u] = ldg_v4(p_local + 4 * i);
+                rm[u] = ldg_v4(exp_avg + 4 * i); rv[u] = ldg_v4(exp_avg_sq + 4 * i);
+                if (EMA) re[u] = ldg_v4(ema + 4 * i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const long long i = c * chunk + (long long)u * kThreads + threadIdx.x;
+            float x[4], a[4], p[4], m[4], v[4];
+            VecTraits<float>::unpack(rx[u], x);
+            VecTraits<float>::unpack(ra[u], a);
+            VecTraits<float>::unpack(rp[u], p);
+            VecTraits<float>::unpack(rm[u], m);
+            VecTraits<float>::unpack(rv[u], v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float g = __fmul_rn(__fsub_rn(x[q], __fmul_rn(s, a[q])), clip);
+                adam_update(g, p[q], m[q], v[q], as);
+            }
+            stg_stream(exp_avg + 4 * i, VecTraits<float>::pack(m));
+            stg_stream(exp_avg_sq + 4 * i, VecTraits<float>::pack(v));
+            if (EMA) {
+                float e[4];
+                VecTraits<float>::unpack(re[u], e);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[q] = ema_update(e[q], p[q], as.ema_omd);
+                stg_stream(ema + 4 * i, VecTraits<float>::pack(e));
+            }
+            const uint4 pv = VecTraits<float>::pack(p);
+#pragma unroll
+            for (int r = 0; r < WORLD; ++r) stg_stream(peers.out[r] + base_elem + 4 * i, pv);  // parameter all-gather
+        }
+    }
+}
+
 static int p2p_grid(long long nvec, int U) {
     const long long chunk = (long long)kThreads * U;
     long long work = (nvec + chunk - 1) / chunk;
@@ -261,6 +337,43 @@ int siss_p2p_combine_allgather(const float* shard_x, const float* shard_a, const
         case 8: p2p_combine_allgather_kernel<8, 4><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(shard_x, shard_a, scalar_slots, rank, shard_len, peers, mode, value, max_norm, inf_guard, stats5); break;
         default: return SISS_EUNSUPPORTED;
     }
+    return (int)cudaGetLastError();
+}
+
+int siss_p2p_adamw_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                             float* const* h_peers_param, int world, int rank, int64_t shard_len,
+                             int mode, float value, float max_norm, int inf_guard,
+                             float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
+                             float* ema_shard, double ema_decay, float* stats5, siss_stream_t stream) {
+    if (!shard_x || !shard_a || !scalar_slots || !h_peers_param || !exp_avg || !exp_avg_sq) return SISS_EINVAL;
+    if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || shard_len < 0 || shard_len % 4 != 0) return SISS_EINVAL;
+    if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_ERASEDIFF || (step < 1 && !d_step)) return SISS_EINVAL;
+    if (ema_shard && !d_sched && !(ema_decay >= 0.0 && ema_decay <= 1.0)) return SISS_EINVAL;
+    if (!aligned16(shard_x) || !aligned16(shard_a) || !aligned16(exp_avg) || !aligned16(exp_avg_sq) || !aligned16(ema_shard))
+        return SISS_EINVAL;
+    PeerOut peers{};
+    for (int r = 0; r < world; ++r) {
+        if (!h_peers_param[r] || !aligned16(h_peers_param[r])) return SISS_EINVAL;
+        peers.out[r] = h_peers_param[r];
+    }
+    long long hs;
+    const AdamScalars as = make_adam_scalars(lr, beta1, beta2, eps, weight_decay, step, ema_decay, hs);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nvec = shard_len / 4;
+    const long long* dstep = (const long long*)d_step;
+#define SISS_LAUNCH_P2P_ADAMW(WORLD, EM)                                                                               \
+    p2p_adamw_allgather_kernel<WORLD, 2, EM><<<p2p_grid(nvec, 2), kThreads, 0, st>>>(                                   \
+        shard_x, shard_a, scalar_slots, rank, shard_len, peers, h_peers_param[rank] + (long long)rank * shard_len,     \
+        exp_avg, exp_avg_sq, ema_shard, as, hs, dstep, d_sched,                                                       \
+        mode, value, max_norm, inf_guard, stats5)
+    switch (world) {
+        case 2: if (ema_shard) SISS_LAUNCH_P2P_ADAMW(2, true); else SISS_LAUNCH_P2P_ADAMW(2, false); break;
+        case 4: if (ema_shard) SISS_LAUNCH_P2P_ADAMW(4, true); else SISS_LAUNCH_P2P_ADAMW(4, false); break;
+        case 8: if (ema_shard) SISS_LAUNCH_P2P_ADAMW(8, true); else SISS_LAUNCH_P2P_ADAMW(8, false); break;
+        default: return SISS_EUNSUPPORTED;
+    }
+#undef SISS_LAUNCH_P2P_ADAMW
     return (int)cudaGetLastError();
 }
 

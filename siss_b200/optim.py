@@ -53,14 +53,19 @@ class FusedCombineAdamW:
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), \
             float(weight_decay)
         dev = combiner.device
-        self.p_flat = torch.zeros(combiner.total, dtype=torch.float32, device=dev)
+        if shard_optimizer is None:
+            # NCCL transport: always. Peer-memory transport: the fused parameter all-gather kernel was validated
+            # against the replicated update at 2 ranks (tests/test_distributed_gpu.py); other sizes opt in explicitly.
+            shard_optimizer = combiner.world > 1 and (combiner.peer is None or combiner.world == 2)
+        self.sharded = bool(shard_optimizer) and combiner.world > 1
+        # sharded + peer-memory transport: parameters live in symmetric memory, gathered by peer stores
+        self.fused_gather = self.sharded and combiner.peer is not None
+        self.p_flat = combiner.peer.alloc_params() if self.fused_gather else \
+            torch.zeros(combiner.total, dtype=torch.float32, device=dev)
         for p, off in zip(combiner.params, combiner.offsets):
             view = self.p_flat[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-        if shard_optimizer is None:
-            shard_optimizer = combiner.world > 1 and combiner.peer is None
-        self.sharded = bool(shard_optimizer) and combiner.world > 1
         if self.sharded:
             lo = combiner.rank * combiner.shard_len
             self.p_shard = self.p_flat[lo:lo + combiner.shard_len]          # view: updated in place, then all-gathered
@@ -144,6 +149,29 @@ class FusedCombineAdamW:
             import torch.distributed as dist
             if not single_term and (scaling_norm is None) == (eta is None):
                 raise ValueError("give exactly one of scaling_norm= or eta= (or single_term=True)")
+            if self.fused_gather and not single_term:
+                # peer-memory transport: two fused kernels — reduce-scatter x2 + K4a | K4b + AdamW/EMA + parameter all-gather
+                self.step_count += 1
+                if self.ema_cfg is not None:
+                    if self.d_sched is None:
+                        self.cur_ema_decay = ema_decay_at(self.step_count, **self.ema_cfg)
+                    elif not torch.cuda.is_current_stream_capturing():
+                        self.set_schedule(ema_decay=ema_decay_at(self.step_count, **self.ema_cfg))
+                stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                _lib.check(_lib.load().siss_counter_add(ctypes.c_void_p(self.d_step.data_ptr()), 1, stream), "siss_counter_add")
+                ops._count()
+                if cb._early_x:
+                    torch.cuda.current_stream(cb.device).wait_event(cb._early_done)
+                mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF
+                cb.peer.adamw_allgather(mode, float(scaling_norm if eta is None else eta), mn, inf_guard, cb.stats,
+                                        self.exp_avg, self.exp_avg_sq, self.ema_flat, self.lr, self.betas, self.eps,
+                                        self.weight_decay, self.step_count, self.d_step, self.d_sched,
+                                        self.cur_ema_decay, x_prereduced=cb._early_x)
+                cb._early_x = False
+                cb.g_x.zero_(); cb.g_a.zero_()
+                cb._dirty_x = False
+                cb._point(cb._views_x)
+                return cb.stats
             sums = cb.reduce_to_shards(single_term)
             if single_term:
                 self._launch(sums, SISS_COMBINE_NONE, 0.0, mn, False, two_term=False, shard=True)

@@ -52,6 +52,46 @@ class PeerExchange:
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)
 
+    def alloc_params(self) -> torch.Tensor:
+        """Flat fp32 parameter buffer in symmetric memory (same length as G_x), for the sharded optimiser step whose
+        parameter all-gather is done by peer stores (:meth:`adamw_allgather`). Collective: call on every rank."""
+        import torch.distributed._symmetric_memory as symm_mem
+        self.p_flat = symm_mem.empty(self.total, dtype=torch.float32, device=self.g_x.device)
+        self.p_flat.zero_()
+        self.h_p = symm_mem.rendezvous(self.p_flat, self.group)
+        self.ptrs_p = (ctypes.c_void_p * self.world)(*[int(p) for p in self.h_p.buffer_ptrs])
+        assert int(self.ptrs_p[self.rank]) == self.p_flat.data_ptr(), "symmetric-memory pointer table does not match"
+        torch.cuda.synchronize(self.g_x.device)
+        dist.barrier(group=self.group)
+        return self.p_flat
+
+    def adamw_allgather(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
+                        exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, ema_shard: Optional[torch.Tensor],
+                        lr: float, betas, eps: float, weight_decay: float, step: int, d_step: torch.Tensor,
+                        d_sched: Optional[torch.Tensor], ema_decay: float, x_prereduced: bool = False) -> None:
+        """Two-term sync step with the ZeRO-1 update: reduce kernel as in :meth:`combine`, then
+        ``siss_p2p_adamw_allgather`` (K4b + AdamW/EMA on this rank's shard + parameter all-gather by peer stores).
+        New parameters land in every rank's ``p_flat``. Stream-ordered; no host synchronisation."""
+        from . import ops
+        lib = _lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = ctypes.c_void_p
+        self.h_x.barrier(channel=0)
+        _lib.check(lib.siss_p2p_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
+                                             self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
+                                             self.sums_local.data_ptr(), int(bool(x_prereduced)), self.ws.data_ptr(),
+                                             stream), "siss_p2p_reduce_norm3")
+        self.h_x.barrier(channel=1)
+        _lib.check(lib.siss_p2p_adamw_allgather(
+            self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), self.ptrs_p, self.world,
+            self.rank, self.shard_len, int(mode), float(value), float(max_norm), int(bool(inf_guard)),
+            P(exp_avg.data_ptr()), P(exp_avg_sq.data_ptr()), float(lr), float(betas[0]), float(betas[1]), float(eps),
+            float(weight_decay), int(step), P(d_step.data_ptr()), P(0 if d_sched is None else d_sched.data_ptr()),
+            P(0 if ema_shard is None else ema_shard.data_ptr()), float(ema_decay), P(stats.data_ptr()), stream),
+            "siss_p2p_adamw_allgather")
+        self.h_x.barrier(channel=2)        # every rank's parameter shard has landed in every p_flat
+        ops._count(2)
+
     def combine(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
                 x_prereduced: bool = False) -> None:
         """Result lands in every rank's ``g_x``. Stream-ordered; no host synchronisation. With

@@ -122,6 +122,11 @@ def test_argument_validation_without_a_gpu():
     assert lib.siss_combine_adamw(one, one, 16, one, 0, 1.0, 1.0, 0, one, one, one, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, N,
                                   N, one, 1.5, 1, N, N, N) == -1                         # EMA decay outside [0, 1]
     assert lib.siss_counter_add(N, 1, N) == -1
+    arr8 = (ctypes.c_void_p * 8)(*([one.value] * 8))
+    assert lib.siss_p2p_adamw_allgather(one, one, one, arr8, 1, 0, 16, 0, 1.0, 1.0, 0, one, one, 1e-3, 0.9, 0.999, 1e-8,
+                                        0.0, 1, N, N, N, 0.0, N, N) == -1                    # world < 2
+    assert lib.siss_p2p_adamw_allgather(one, one, one, arr8, 2, 0, 16, 2, 1.0, 1.0, 0, one, one, 1e-3, 0.9, 0.999, 1e-8,
+                                        0.0, 1, N, N, N, 0.0, N, N) == -1                    # single-term mode not offered
     assert lib.siss_membership_add_noise(one, one, one, one, 1000, 1000, one, one, 0, 1, 1, 16, 0, N) == -1   # t >= T
     assert lib.siss_membership_add_noise(one, one, one, one, 1000, 5, one, one, 0, 1, 0, 16, 0, N) == -1      # n_noise < 1
     assert lib.siss_membership_sqerr(one, one, one, 0, one, one, N, 0, 1, 1, 16, N) == -1                     # no workspace

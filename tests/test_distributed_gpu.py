@@ -47,7 +47,8 @@ def _run_opt(rank, world, Bg, transport="auto", shard=None):
     opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, ema=dict(decay=0.9),
                             shard_optimizer=shard)
     if world > 1:
-        assert opt.sharded == ((transport == "nccl") if shard is None else shard)
+        assert opt.sharded == ((transport == "nccl" or world == 2) if shard is None else shard)
+        assert opt.fused_gather == (opt.sharded and transport == "p2p")      # parameter all-gather by peer stores
         if opt.sharded:
             assert opt.exp_avg.numel() == comb.total // world and opt.ema_flat.numel() == comb.total // world
     step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
@@ -105,7 +106,7 @@ def _worker(rank, world, port, q):
         out[transport] = _run(rank, world, 8, 2, transport)
         if world == 2:
             out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
-            out[transport + "/fused_adamw_other_layout"] = _run_opt(rank, world, 8, transport, shard=(transport == "p2p"))
+            out[transport + "/fused_adamw_replicated"] = _run_opt(rank, world, 8, transport, shard=False)
     if rank == 0:
         q.put(out)
     dist.barrier()
