@@ -54,9 +54,10 @@ class FusedCombineAdamW:
             float(weight_decay)
         dev = combiner.device
         if shard_optimizer is None:
-            # NCCL transport: always. Peer-memory transport: the fused parameter all-gather kernel was validated
-            # against the replicated update at 2 ranks (tests/test_distributed_gpu.py); other sizes opt in explicitly.
-            shard_optimizer = combiner.world > 1 and (combiner.peer is None or combiner.world == 2)
+            # NCCL transport: always. Peer-memory transport: the fused parameter all-gather kernel is validated
+            # against the replicated update at 2 and 4 ranks (tests/test_distributed_gpu.py); 8 ranks opt in explicitly
+            # (transport "auto" picks NCCL there anyway).
+            shard_optimizer = combiner.world > 1 and (combiner.peer is None or combiner.world in (2, 4))
         self.sharded = bool(shard_optimizer) and combiner.world > 1
         # sharded + peer-memory transport: parameters live in symmetric memory, gathered by peer stores
         self.fused_gather = self.sharded and combiner.peer is not None

@@ -47,7 +47,7 @@ def _run_opt(rank, world, Bg, transport="auto", shard=None):
     opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, ema=dict(decay=0.9),
                             shard_optimizer=shard)
     if world > 1:
-        assert opt.sharded == ((transport == "nccl" or world == 2) if shard is None else shard)
+        assert opt.sharded == ((transport == "nccl" or world in (2, 4)) if shard is None else shard)
         assert opt.fused_gather == (opt.sharded and transport == "p2p")      # parameter all-gather by peer stores
         if opt.sharded:
             assert opt.exp_avg.numel() == comb.total // world and opt.ema_flat.numel() == comb.total // world
@@ -104,7 +104,7 @@ def _worker(rank, world, port, q):
     out = {}
     for transport in ("nccl", "p2p"):
         out[transport] = _run(rank, world, 8, 2, transport)
-        if world == 2:
+        if world in (2, 4):
             out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
             out[transport + "/fused_adamw_replicated"] = _run_opt(rank, world, 8, transport, shard=False)
     if rank == 0:
@@ -128,7 +128,7 @@ def test_multi_gpu_step_equals_single_gpu(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     flat1, stats1 = _run(0, 1, 8, 2)
-    params1 = _run_opt(0, 1, 8) if world == 2 else None
+    params1 = _run_opt(0, 1, 8) if world in (2, 4) else None
     for transport, res in out.items():                  # NCCL collectives and fused NVLink peer-memory kernels
         if "/fused_adamw" in transport:                 # replicated and ZeRO-1 sharded layouts, parameters + EMA shadow
             torch.testing.assert_close(res, params1, rtol=3e-5, atol=3e-6, msg=lambda m: f"{transport}: {m}")
