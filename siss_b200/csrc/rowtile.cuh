@@ -11,10 +11,12 @@
 // open; a CTA touches at most span/row_len + 2 rows.
 //
 // Rows that are split over several CTAs combine their partial sums through a small workspace:
-//   slot(cta c, row r) = c + r      (unique, because spans and rows are both monotone; < grid + B)
-//   contributors of row r = owner(first unit of r) .. owner(last unit of r)   (consecutive CTAs)
+//   a span has at most two row segments shared with other spans (its first and its last row), so it owns
+//   two partial slots: slot(span c, segment) = 2c if the row began before the span, 2c + 1 otherwise
+//   contributors of row r = owner(first unit of r) .. owner(last unit of r)   (consecutive spans)
 // The last contributor to arrive (ticket counter per row) sums the slots in fixed order with one
 // warp (lane-strided, then butterfly), so results are bitwise reproducible for a given shape+GPU.
+// The layout does not depend on the batch size of the call (see RowWorkspace below).
 #pragma once
 
 #include "common.cuh"
