@@ -264,7 +264,7 @@ int siss_counter_add(int64_t* d_counter, int64_t value, siss_stream_t stream);
  * torch.randint (:593) and the CPU `torch.rand(B) > lambd` with its H2D copy
  * (losses/ddpm_deletion_loss.py:18). This is a NEW seed semantic (hence opt-in): a value depends only on
  * (seed, draw, global element / row index), so data-parallel ranks passing their global offsets draw exactly
- * the slices of the 1-rank tensors. `draw` (< 2^63) names one independent draw, e.g. the micro-step index;
+ * the slices of the 1-rank tensors. `draw` (< 2^62) names one independent draw, e.g. the micro-step index;
  * d_draw (nullable): read the draw index from this DEVICE uint64 instead (advance it on the stream with
  * siss_counter_add), so a captured CUDA graph draws fresh values on every replay.
  *   siss_randn      : out[i] = N(0,1) sample of global element elem_offset + i, rounded to `dtype`;
@@ -285,6 +285,15 @@ int siss_add_noise_mixture_rng(const void* x0, const void* a0, const uint8_t* ke
                                double lambd, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
                                void* x_mix, void* noise_out, float* dist_x, float* dist_a, float* w_x, float* w_a,
                                void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream);
+/* EraseDiff with the forget target drawn in-kernel (opt-in device RNG): siss_dual_mse_fwd_bwd where target_a is not
+ * read but generated — uniform [0, 1) from the aux domain of the same stream, rounded to the prediction dtype, like
+ * torch.rand_like(eps_hat_a) (losses/ddpm_deletion_loss.py:75). 16 + s bytes/element instead of 20 + the rand_like
+ * launch's 4. target_a_out (nullable, prediction dtype) also materialises the target. */
+int siss_dual_mse_rng_fwd_bwd(const void* pred_x, const void* pred_a, int pred_dtype, const void* target_x, int target_dtype,
+                              uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
+                              float go_x, float go_a, void* grad_x, void* grad_a, void* target_a_out,
+                              float* row_loss_x, float* row_loss_a, void* workspace, int64_t B, int64_t D,
+                              siss_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Membership-loss metric (metrics/class_membership.py:66-116): I sampled images x n_noise shared noise

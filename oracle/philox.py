@@ -12,10 +12,13 @@ seed semantic, so there is no reference output to pin. What is pinned instead:
 Stream definition (shared with csrc/philox.cuh):
   key      = (seed & 0xffffffff, seed >> 32)
   noise    : counter = (c & 0xffffffff, c >> 32, draw & 0xffffffff, draw >> 32), c = global_element_index // 4,
-             draw < 2**63; the call's four words give elements 4c .. 4c+3:
+             draw < 2**62; the call's four words give elements 4c .. 4c+3:
              (z0, z1) = box_muller(w0, w1), (z2, z3) = box_muller(w2, w3)
   per row  : counter = (r & 0xffffffff, r >> 32, draw & 0xffffffff, (draw >> 32) | 0x80000000), r = global row index;
              t = t_lo + w0 % (t_hi - t_lo);  keep = uniform(w1) > lambd        (torch.rand(B) > lambd, :18)
+  aux      : counter = (c & 0xffffffff, c >> 32, draw & 0xffffffff, (draw >> 32) | 0x40000000): a second element-indexed
+             tensor of the same draw (EraseDiff's uniform forget target, losses/ddpm_deletion_loss.py:75);
+             element e takes word e % 4 of call e // 4, u = (w >> 8) * 2**-24 in [0, 1)
   uniform(w)    = float32(w) * 2**-32 + 2**-33                  in (0, 1]
   box_muller(a, b): rad = sqrt(-2 ln uniform(a)); ang = 2 pi uniform(b); (rad cos ang, rad sin ang)
 """
@@ -54,7 +57,7 @@ def noise_words(n: int, seed: int, draw: int, elem_offset: int = 0) -> np.ndarra
     """The uint32 word behind each of the n elements [elem_offset, elem_offset + n)."""
     e = np.arange(elem_offset, elem_offset + n, dtype=np.uint64)
     c = e >> np.uint64(2)
-    ctr = np.stack([c & MASK, c >> np.uint64(32), np.full_like(c, draw & 0xFFFFFFFF), np.full_like(c, (draw >> 32) & 0x7FFFFFFF)],
+    ctr = np.stack([c & MASK, c >> np.uint64(32), np.full_like(c, draw & 0xFFFFFFFF), np.full_like(c, (draw >> 32) & 0x3FFFFFFF)],
                    axis=-1)
     out = philox4x32_10(ctr, _key(seed))
     return out, (e & np.uint64(3)).astype(np.int64)
@@ -75,8 +78,19 @@ def draw_rows(B: int, seed: int, draw: int, t_lo: int, t_hi: int, lambd: float, 
     """(timesteps int64 [B], keep bool [B]) of global rows [row_offset, row_offset + B)."""
     r = np.arange(row_offset, row_offset + B, dtype=np.uint64)
     ctr = np.stack([r & MASK, r >> np.uint64(32), np.full_like(r, draw & 0xFFFFFFFF),
-                    np.full_like(r, ((draw >> 32) & 0x7FFFFFFF) | 0x80000000)], axis=-1)
+                    np.full_like(r, ((draw >> 32) & 0x3FFFFFFF) | 0x80000000)], axis=-1)
     w = philox4x32_10(ctr, _key(seed))
     t = t_lo + (w[:, 0].astype(np.int64) % (t_hi - t_lo))
     keep = uniform32(w[:, 1]) > np.float32(lambd)
     return t, keep
+
+
+def rand_aux(n: int, seed: int, draw: int, elem_offset: int = 0) -> np.ndarray:
+    """float32 uniforms in [0, 1) of the aux stream for elements [elem_offset, elem_offset + n) — exact."""
+    e = np.arange(elem_offset, elem_offset + n, dtype=np.uint64)
+    c = e >> np.uint64(2)
+    ctr = np.stack([c & MASK, c >> np.uint64(32), np.full_like(c, draw & 0xFFFFFFFF),
+                    np.full_like(c, ((draw >> 32) & 0x3FFFFFFF) | 0x40000000)], axis=-1)
+    words = philox4x32_10(ctr, _key(seed))
+    w = np.take_along_axis(words, (e & np.uint64(3)).astype(np.int64)[:, None], axis=1)[:, 0]
+    return (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)

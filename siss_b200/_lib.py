@@ -51,6 +51,7 @@ SIGNATURES = {
     "siss_randn": (_I, [_P, _L, _I, _U, _U, _P, _U, _P]),
     "siss_draw_rows": (_I, [_P, _P, _L, _U, _U, _P, _U, _L, _L, _D, _P]),
     "siss_add_noise_mixture_rng": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _D, _U, _U, _P, _U, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "siss_dual_mse_rng_fwd_bwd": (_I, [_P, _P, _I, _P, _I, _U, _U, _P, _U, _F, _F, _P, _P, _P, _P, _P, _P, _L, _L, _P]),
     "siss_membership_add_noise": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _L, _L, _L, _L, _I, _P]),
     "siss_membership_sqerr": (_I, [_P, _P, _P, _I, _P, _P, _P, _L, _L, _L, _L, _P]),
     "siss_batch_stats": (_I, [_P, _P, _P, _P, _L, _L, _P, _P]),

@@ -4,6 +4,9 @@
 //   noise   : counter = (c lo, c hi, draw lo, draw hi [bit 31 clear]), c = global element index / 4; the four
 //             words of call c give elements 4c..4c+3: (z0,z1) = box_muller(w0,w1), (z2,z3) = box_muller(w2,w3)
 //   per row : counter = (row lo, row hi, draw lo, draw hi | 0x80000000)
+//   aux     : counter = (c lo, c hi, draw lo, draw hi | 0x40000000) — a second element-indexed tensor of the same draw
+//             (EraseDiff's uniform forget target): element e takes word e % 4 of call e / 4, u = (w >> 8) * 2^-24 in [0, 1)
+// draw < 2^62 (bits 30 and 31 of the high word select the domain).
 // Every value is a pure function of (seed, draw, global index): independent of grid, scheduling, sharding.
 #pragma once
 
@@ -13,13 +16,15 @@ namespace siss {
 
 struct RngStream {
     uint32_t k0, k1;   // key   = seed
-    uint32_t d0, d1;   // draw  (d1 bit 31 selects the per-row domain)
+    uint32_t d0, d1;   // draw  (d1 bits 31 / 30 select the per-row / aux domain)
 };
 
-__host__ __device__ inline RngStream make_rng_stream(uint64_t seed, uint64_t draw, bool row_domain) {
+enum RngDomain : uint32_t { kRngNoise = 0u, kRngRows = 0x80000000u, kRngAux = 0x40000000u };
+
+__host__ __device__ inline RngStream make_rng_stream(uint64_t seed, uint64_t draw, uint32_t domain) {
     RngStream r;
     r.k0 = (uint32_t)seed; r.k1 = (uint32_t)(seed >> 32);
-    r.d0 = (uint32_t)draw; r.d1 = ((uint32_t)(draw >> 32) & 0x7FFFFFFFu) | (row_domain ? 0x80000000u : 0u);
+    r.d0 = (uint32_t)draw; r.d1 = ((uint32_t)(draw >> 32) & 0x3FFFFFFFu) | domain;
     return r;
 }
 
@@ -29,7 +34,7 @@ __device__ __forceinline__ void rng_draw_from_device(RngStream& s, const unsigne
     if (d_draw != nullptr) {
         const unsigned long long d = *d_draw;
         s.d0 = (uint32_t)d;
-        s.d1 = ((uint32_t)(d >> 32) & 0x7FFFFFFFu) | (s.d1 & 0x80000000u);
+        s.d1 = ((uint32_t)(d >> 32) & 0x3FFFFFFFu) | (s.d1 & 0xC0000000u);
     }
 }
 
@@ -50,6 +55,29 @@ __device__ __forceinline__ void philox4x32_10(const RngStream& s, unsigned long 
 // (w + 0.5) / 2^32 in (0, 1]: the product is exact (power-of-two scale), one rounding in the add
 __device__ __forceinline__ float rng_uniform(uint32_t w) {
     return __fadd_rn(__fmul_rn(__uint2float_rn(w), 2.3283064365386963e-10f), 1.1641532182693481e-10f);
+}
+
+// 24-bit uniform in [0, 1), exactly representable (what torch.rand's fp32 values look like)
+__device__ __forceinline__ float rng_uniform01(uint32_t w) { return __uint2float_rn(w >> 8) * 5.9604644775390625e-08f; }
+
+// W consecutive uniforms in [0, 1) starting at global element e0 (aux domain stream).
+template <int W>
+__device__ __forceinline__ void rng_uniforms(const RngStream& s, unsigned long long e0, float (&u)[W]) {
+    if constexpr (W == 1) {
+        uint32_t w[4];
+        philox4x32_10(s, e0 >> 2, w);
+        const int lane = (int)(e0 & 3ull);
+        u[0] = rng_uniform01(lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]);
+    } else {
+        static_assert(W % 4 == 0, "vector widths are multiples of one Philox call");
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+            uint32_t w[4];
+            philox4x32_10(s, (e0 >> 2) + i, w);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[4 * i + q] = rng_uniform01(w[q]);
+        }
+    }
 }
 
 // Hardware transcendental units (MUFU.LG2 / MUFU.SIN / MUFU.COS): absolute error ~2^-21, far below what a

@@ -52,7 +52,7 @@ static int launch_randn(void* out, long long n, uint64_t seed, uint64_t draw, co
     const long long cap = (long long)cached_sm_count() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    randn_kernel<T><<<(int)grid, kThreads, 0, st>>>((T*)out, n, nvec, make_rng_stream(seed, draw, false),
+    randn_kernel<T><<<(int)grid, kThreads, 0, st>>>((T*)out, n, nvec, make_rng_stream(seed, draw, kRngNoise),
                                                     (const unsigned long long*)d_draw, elem_offset);
     return (int)cudaGetLastError();
 }
@@ -65,7 +65,7 @@ extern "C" {
 
 int siss_randn(void* out, int64_t n, int dtype, uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
                siss_stream_t stream) {
-    if (!out || n < 0 || (draw >> 63)) return SISS_EINVAL;
+    if (!out || n < 0 || (draw >> 62)) return SISS_EINVAL;
     if (n == 0) return SISS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
@@ -78,12 +78,12 @@ int siss_randn(void* out, int64_t n, int dtype, uint64_t seed, uint64_t draw, co
 
 int siss_draw_rows(int64_t* timesteps, uint8_t* keep_mask, int64_t B, uint64_t seed, uint64_t draw, const uint64_t* d_draw,
                    uint64_t row_offset, int64_t t_lo, int64_t t_hi, double lambd, siss_stream_t stream) {
-    if ((!timesteps && !keep_mask) || B < 0 || (draw >> 63)) return SISS_EINVAL;
+    if ((!timesteps && !keep_mask) || B < 0 || (draw >> 62)) return SISS_EINVAL;
     if (timesteps && (t_lo < 0 || t_hi <= t_lo || t_hi - t_lo > 0x7FFFFFFFLL)) return SISS_EINVAL;
     if (B == 0) return SISS_OK;
     const unsigned int span = timesteps ? (unsigned int)(t_hi - t_lo) : 1u;
     draw_rows_kernel<<<(int)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        B, make_rng_stream(seed, draw, true), (const unsigned long long*)d_draw, row_offset, t_lo, span, (float)lambd,
+        B, make_rng_stream(seed, draw, kRngRows), (const unsigned long long*)d_draw, row_offset, t_lo, span, (float)lambd,
         timesteps, keep_mask);
     return (int)cudaGetLastError();
 }

@@ -437,13 +437,13 @@ int siss_add_noise_mixture_rng(const void* x0, const void* a0, const uint8_t* ke
                                void* x_mix, void* noise_out, float* dist_x, float* dist_a, float* w_x, float* w_a,
                                void* workspace, int64_t B, int64_t D, int dtype, siss_stream_t stream) {
     if (!x0 || !a0 || !keep_mask || !timesteps || !alphas_cumprod || !gamma || !sigma || !x_mix ||
-        !dist_x || !dist_a || !w_x || !w_a || !workspace || B < 0 || D < 1 || T_steps < 1 || (draw >> 63))
+        !dist_x || !dist_a || !w_x || !w_a || !workspace || B < 0 || D < 1 || T_steps < 1 || (draw >> 62))
         return SISS_EINVAL;
     if (B == 0) return SISS_OK;
     SISS_DISPATCH_DTYPE(dtype, (launch_mixture<T, true, true>(nullptr, nullptr, x0, a0, nullptr, keep_mask, timesteps,
                                                               alphas_cumprod, gamma, sigma, T_steps, lambd, x_mix, dist_x,
                                                               dist_a, w_x, w_a, workspace, B, D, (cudaStream_t)stream,
-                                                              make_rng_stream(seed, draw, false),
+                                                              make_rng_stream(seed, draw, kRngNoise),
                                                               (const unsigned long long*)d_draw, elem_offset, noise_out)));
 }
 

@@ -7,6 +7,7 @@
 // reduction order.
 
 #include "bulkpipe.cuh"
+#include "philox.cuh"
 
 namespace siss {
 
@@ -379,19 +380,25 @@ sqerr_bwd_kernel(const TP* __restrict__ pred, const TT* __restrict__ tgt,
 // ---------------------------------------------------------------------------------------------
 // Dual MSE fast path (No-IS / EraseDiff): two preds, one or two targets, both grads + row sums.
 // ---------------------------------------------------------------------------------------------
-template <typename TP, typename TT, int W, bool VEC>
+// RNG_A (opt-in device RNG, EraseDiff): the forget target is not read but drawn in registers — uniform [0, 1) from the
+// aux domain of the counter-based stream, rounded to the prediction dtype like torch.rand_like(eps_hat_a)
+// (losses/ddpm_deletion_loss.py:75) — and optionally written to tgt_a_out.
+template <typename TP, typename TT, int W, bool VEC, bool RNG_A = false>
 __global__ void __launch_bounds__(kThreads, kK3Occ)
 dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
                 const TT* __restrict__ tgt_x, const TT* __restrict__ tgt_a, float go_x, float go_a,
                 TP* __restrict__ grad_x, TP* __restrict__ grad_a,
                 float* __restrict__ row_loss_x, float* __restrict__ row_loss_a,
-                RowWorkspace ws, RowSched rt) {
+                RowWorkspace ws, RowSched rt,
+                RngStream rng = RngStream{0, 0, 0, 0}, const unsigned long long* __restrict__ d_draw = nullptr,
+                unsigned long long elem_offset = 0, TP* __restrict__ tgt_a_out = nullptr) {
     constexpr int VPT = kK3Vpt;
     using PIO = PredIO<TP, W, VEC>;
     using TIO = PredIO<TT, W, VEC>;
     __shared__ float red[2 * kWarps];
     __shared__ int flag;
-    const bool shared_tgt = (tgt_a == tgt_x);
+    const bool shared_tgt = !RNG_A && (tgt_a == tgt_x);
+    if (RNG_A) rng_draw_from_device(rng, d_draw);
 
     long long u0, u1;
     cta_span(rt, u0, u1);
@@ -412,7 +419,7 @@ dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
                     PIO::fetch(pred_x + e[j], rpx[j]);
                     PIO::fetch(pred_a + e[j], rpa[j]);
                     TIO::fetch(tgt_x + e[j], rtx[j]);
-                    if (!shared_tgt) TIO::fetch(tgt_a + e[j], rta[j]);
+                    if (!RNG_A && !shared_tgt) TIO::fetch(tgt_a + e[j], rta[j]);
                 }
             }
 #pragma unroll
@@ -422,7 +429,14 @@ dual_mse_kernel(const TP* __restrict__ pred_x, const TP* __restrict__ pred_a,
                 PIO::decode(rpx[j], px);
                 PIO::decode(rpa[j], pa);
                 TIO::decode(rtx[j], tx);
-                if (!shared_tgt) TIO::decode(rta[j], ta);
+                if constexpr (RNG_A) {
+                    rng_uniforms<W>(rng, elem_offset + (unsigned long long)e[j], ta);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) ta[q] = VecTraits<TP>::round(ta[q]);
+                    if (tgt_a_out) PIO::store(tgt_a_out + e[j], ta);
+                } else if (!shared_tgt) {
+                    TIO::decode(rta[j], ta);
+                }
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
                     const float ux = __fsub_rn(px[q], tx[q]);
@@ -708,6 +722,30 @@ static int launch_dual_mse(const void* pred_x, const void* pred_a, const void* t
     return (int)cudaGetLastError();
 }
 
+template <typename TP, typename TT>
+static int launch_dual_mse_rng(const void* pred_x, const void* pred_a, const void* tgt_x, RngStream rng,
+                               const unsigned long long* d_draw, unsigned long long elem_offset, float go_x, float go_a,
+                               void* grad_x, void* grad_a, void* tgt_a_out, float* row_loss_x, float* row_loss_a,
+                               void* workspace, long long B, long long D, cudaStream_t st) {
+    constexpr int NP = VecTraits<TP>::N, NT = VecTraits<TT>::N;
+    constexpr int W = NP > NT ? NP : NT;
+    RowWorkspace ws = carve_row_workspace(workspace, B);
+    const bool vec = (D % W == 0) && (elem_offset % 4 == 0) && aligned16(pred_x) && aligned16(pred_a) && aligned16(tgt_x) &&
+                     aligned16(grad_x) && aligned16(grad_a) && aligned16(tgt_a_out);
+    if (vec) {
+        RowSched rt = make_row_sched(B, D, W, kK3Occ);
+        dual_mse_kernel<TP, TT, W, true, true><<<rt.grid, kThreads, 0, st>>>(
+            (const TP*)pred_x, (const TP*)pred_a, (const TT*)tgt_x, nullptr, go_x, go_a, (TP*)grad_x, (TP*)grad_a,
+            row_loss_x, row_loss_a, ws, rt, rng, d_draw, elem_offset, (TP*)tgt_a_out);
+    } else {
+        RowSched rt = make_row_sched(B, D, 1, kK3Occ);
+        dual_mse_kernel<TP, TT, 1, false, true><<<rt.grid, kThreads, 0, st>>>(
+            (const TP*)pred_x, (const TP*)pred_a, (const TT*)tgt_x, nullptr, go_x, go_a, (TP*)grad_x, (TP*)grad_a,
+            row_loss_x, row_loss_a, ws, rt, rng, d_draw, elem_offset, (TP*)tgt_a_out);
+    }
+    return (int)cudaGetLastError();
+}
+
 static int flat_grid(long long n_items) {
     long long blocks = (n_items + kThreads - 1) / kThreads;
     const long long cap = (long long)cached_sm_count() * 8;
@@ -811,6 +849,20 @@ int siss_dual_mse_fwd_bwd(const void* pred_x, const void* pred_a, int pred_dtype
     if (B == 0) return SISS_OK;
     SISS_DISPATCH_PRED_IN(pred_dtype, target_dtype, launch_dual_mse, pred_x, pred_a, target_x, target_a, go_x, go_a,
                           grad_x, grad_a, row_loss_x, row_loss_a, workspace, B, D, (cudaStream_t)stream);
+}
+
+int siss_dual_mse_rng_fwd_bwd(const void* pred_x, const void* pred_a, int pred_dtype, const void* target_x, int target_dtype,
+                              uint64_t seed, uint64_t draw, const uint64_t* d_draw, uint64_t elem_offset,
+                              float go_x, float go_a, void* grad_x, void* grad_a, void* target_a_out,
+                              float* row_loss_x, float* row_loss_a, void* workspace, int64_t B, int64_t D,
+                              siss_stream_t stream) {
+    if (!pred_x || !pred_a || !target_x || !grad_x || !grad_a || !row_loss_x || !row_loss_a || !workspace || B < 0 ||
+        D < 1 || (draw >> 62))
+        return SISS_EINVAL;
+    if (B == 0) return SISS_OK;
+    SISS_DISPATCH_PRED_IN(pred_dtype, target_dtype, launch_dual_mse_rng, pred_x, pred_a, target_x,
+                          make_rng_stream(seed, draw, kRngAux), (const unsigned long long*)d_draw, elem_offset, go_x, go_a,
+                          grad_x, grad_a, target_a_out, row_loss_x, row_loss_a, workspace, B, D, (cudaStream_t)stream);
 }
 
 // promoted output dtype of (pred, target): fp32 unless both are the same 16-bit type

@@ -381,6 +381,29 @@ def dual_mse_fwd_bwd(pred_x, pred_a, target_x, target_a, go_x: float, go_a: floa
     return grad_x, grad_a, rows[0], rows[1]
 
 
+def dual_mse_rng_fwd_bwd(pred_x, pred_a, target_x, go_x: float, go_a: float, seed: int, draw: int, elem_offset: int = 0,
+                         d_draw: Optional[torch.Tensor] = None, want_target: bool = False):
+    """EraseDiff fast path with the uniform forget target drawn in-kernel from the counter-based stream (opt-in,
+    siss_b200.rng). Returns (grad_x, grad_a, row_loss_x, row_loss_a, target_a-or-None)."""
+    dev = _need_cuda(pred_x, pred_a, target_x)
+    if not (pred_x.shape == pred_a.shape == target_x.shape) or pred_x.dtype != pred_a.dtype:
+        raise ValueError("pred_x, pred_a and target_x must share one shape; preds share a dtype")
+    pred_x, pred_a, target_x = _c(pred_x), _c(pred_a), _c(target_x)
+    B, D = _rows(pred_x)
+    grad_x, grad_a = torch.empty_like(pred_x), torch.empty_like(pred_a)
+    tgt = torch.empty_like(pred_a) if want_target else None
+    rows = torch.empty((2, B), dtype=torch.float32, device=dev)
+    if pred_x.numel() == 0:
+        return grad_x, grad_a, rows[0].zero_(), rows[1].zero_(), tgt
+    ws = _row_workspace(dev, B)
+    _lib.check(_lib.load().siss_dual_mse_rng_fwd_bwd(
+        _ptr(pred_x), _ptr(pred_a), _dt(pred_x), _ptr(target_x), _dt(target_x), int(seed) & 0xFFFFFFFFFFFFFFFF,
+        int(draw), _ptr(d_draw), int(elem_offset), float(go_x), float(go_a), _ptr(grad_x), _ptr(grad_a), _ptr(tgt),
+        _ptr(rows[0]), _ptr(rows[1]), _ptr(ws), B, D, _stream()), "siss_dual_mse_rng_fwd_bwd")
+    _count()
+    return grad_x, grad_a, rows[0], rows[1], tgt
+
+
 # ------------------------------------------------------------------------------------------------
 # K4
 # ------------------------------------------------------------------------------------------------

@@ -59,6 +59,18 @@ class DeviceRng:
         ops._count()
         return out
 
+    def rand_aux(self, shape: Sequence[int], dtype: torch.dtype, device, draw: Optional[int] = None) -> torch.Tensor:
+        """The uniform [0, 1) tensor the in-kernel EraseDiff target uses for this draw (aux domain), materialised —
+        for inspection and tests. Implemented with the kernel itself: zero predictions, target written out."""
+        z = torch.zeros(tuple(shape), dtype=dtype, device=device)
+        if z.numel() == 0:
+            return z
+        per_row = z.numel() // z.shape[0]
+        out = ops.dual_mse_rng_fwd_bwd(z, z, z, 0.0, 0.0, self.seed, self.draw if draw is None else int(draw),
+                                       elem_offset=self.row_offset * per_row,
+                                       d_draw=self.d_draw if draw is None else None, want_target=True)
+        return out[4]
+
     def draw_rows(self, B: int, device, t_range: Optional[Tuple[int, int]] = None, lambd: Optional[float] = None,
                   draw: Optional[int] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """(timesteps int64 [B] uniform in [t_lo, t_hi), keep_mask uint8 [B] = uniform > lambd); either may be

@@ -130,15 +130,24 @@ class UnlearnStep:
             pred_x = self.unet(xt_x, timesteps, **cond, return_dict=False)[0]
             pred_a = self.unet(xt_a, timesteps, **cond, return_dict=False)[0]
             # EraseDiff's forget target: uniform noise drawn after the second forward (ddpm_deletion_loss.py:75)
-            if self.loss_fn == "erasediff":
-                tgt_a = torch.rand_like(pred_a) if forget_target is None else forget_target
+            if self.loss_fn == "erasediff" and forget_target is None and rng is not None:
+                # opt-in device RNG: the uniform target is drawn inside the kernel (aux domain of this micro-step's draw)
+                if draw is None:
+                    draw = rng.next_draw()
+                per_row = x0.numel() // max(x0.shape[0], 1)
+                g_x, g_a, rl_x, rl_a, _ = ops.dual_mse_rng_fwd_bwd(
+                    pred_x.detach(), pred_a.detach(), noise, self.go, self.go, rng.seed, draw,
+                    elem_offset=rng.row_offset * per_row, d_draw=rng.d_draw)
             else:
-                tgt_a = noise
-            tgt_x = noise
-            if tgt_a.dtype != tgt_x.dtype:
-                tgt_x = tgt_x.to(tgt_a.dtype)
-            g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a,
-                                                        self.go, self.go)
+                if self.loss_fn == "erasediff":
+                    tgt_a = torch.rand_like(pred_a) if forget_target is None else forget_target
+                else:
+                    tgt_a = noise
+                tgt_x = noise
+                if tgt_a.dtype != tgt_x.dtype:
+                    tgt_x = tgt_x.to(tgt_a.dtype)
+                g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a,
+                                                            self.go, self.go)
             cb.begin_x()
             torch.autograd.backward(pred_x, g_x)
             cb.begin_a(last_micro_step=last)

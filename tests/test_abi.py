@@ -122,6 +122,9 @@ def test_argument_validation_without_a_gpu():
     assert lib.siss_combine_adamw(one, one, 16, one, 0, 1.0, 1.0, 0, one, one, one, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, N,
                                   N, one, 1.5, 1, N, N, N) == -1                         # EMA decay outside [0, 1]
     assert lib.siss_counter_add(N, 1, N) == -1
+    assert lib.siss_dual_mse_rng_fwd_bwd(one, one, 0, one, 0, 1, 1 << 62, N, 0, 1.0, 1.0, one, one, N, one, one, one, 1, 16,
+                                         N) == -1                                            # draw >= 2^62
+    assert lib.siss_randn(one, 16, 0, 1, 1 << 62, N, 0, N) == -1
     arr8 = (ctypes.c_void_p * 8)(*([one.value] * 8))
     assert lib.siss_p2p_adamw_allgather(one, one, one, arr8, 1, 0, 16, 0, 1.0, 1.0, 0, one, one, 1e-3, 0.9, 0.999, 1e-8,
                                         0.0, 1, N, N, N, 0.0, N, N) == -1                    # world < 2

@@ -43,3 +43,16 @@ def test_stream_statistics():
     _, k1 = P.draw_rows(1000, seed=7, draw=0, t_lo=0, t_hi=1, lambd=1.0)
     _, k0 = P.draw_rows(1000, seed=7, draw=0, t_lo=0, t_hi=1, lambd=0.0)
     assert not k1.any() and k0.all()                                                        # the reference's edge cases
+
+
+def test_aux_uniform_stream():
+    """EraseDiff's in-kernel uniform target: [0, 1), 24-bit, a function of the global index, independent of the
+    noise domain of the same draw."""
+    u = P.rand_aux(400_000, seed=7, draw=0)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3
+    assert np.array_equal(u * np.float32(2 ** 24), np.floor(u * np.float32(2 ** 24)))      # 24-bit grid
+    assert np.array_equal(P.rand_aux(300, seed=7, draw=0, elem_offset=437), u[437:737])
+    words, lane = P.noise_words(4000, seed=7, draw=0)
+    noise_u = (np.take_along_axis(words, lane[:, None], axis=1)[:, 0] >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    assert not np.array_equal(noise_u, u[:4000]) and abs(np.corrcoef(noise_u, u[:4000])[0, 1]) < 5e-2

@@ -152,3 +152,57 @@ def test_unlearn_step_with_device_rng_equals_explicit_draws(loss_fn, kw, dev):
             assert torch.equal(p.grad, q.grad)
     with pytest.raises(ValueError):
         sb.micro_step(x0, a0)                                      # no device_rng and no noise
+
+
+@pytest.mark.parametrize("pred_dtype,tgt_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                                   (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("shape", [(4, 3, 64, 64), (5, 3, 17, 9), (2, 3, 256, 256)])
+def test_erasediff_in_kernel_target(pred_dtype, tgt_dtype, shape, dev):
+    """siss_dual_mse_rng_fwd_bwd: (a) the drawn target equals the oracle's aux stream EXACTLY (24-bit uniforms, rounded
+    to the prediction dtype); (b) gradients / row sums are bit-identical to the existing dual-MSE kernel fed that target."""
+    from siss_b200 import ops
+    from siss_b200.rng import DeviceRng
+    torch.manual_seed(shape[0])
+    B = shape[0]; n = B * shape[1] * shape[2] * shape[3]
+    px = torch.randn(shape).to(pred_dtype).to(dev); pa = torch.randn(shape).to(pred_dtype).to(dev)
+    noise = torch.randn(shape).to(tgt_dtype).to(dev)
+    for row_offset in (0, 3):
+        off = row_offset * (n // B)
+        gx, ga, rlx, rla, tgt = ops.dual_mse_rng_fwd_bwd(px, pa, noise, 0.25, 0.5, 99, 4, elem_offset=off, want_target=True)
+        want_t = torch.from_numpy(P.rand_aux(n, seed=99, draw=4, elem_offset=off)).reshape(shape).to(pred_dtype)
+        assert tgt.dtype == pred_dtype and torch.equal(tgt.cpu(), want_t)
+        assert torch.equal(DeviceRng(99, row_offset=row_offset).rand_aux(shape, pred_dtype, dev, draw=4), tgt)
+        tx = noise if tgt_dtype == pred_dtype else noise.to(pred_dtype)           # the unfused path needs one dtype
+        rgx, rga, rrlx, rrla = ops.dual_mse_fwd_bwd(px, pa, tx, tgt, 0.25, 0.5)
+        assert torch.equal(gx, rgx) and torch.equal(ga, rga)
+        torch.testing.assert_close(rlx, rrlx, rtol=1e-5, atol=0); torch.testing.assert_close(rla, rrla, rtol=1e-5, atol=0)
+        g2 = ops.dual_mse_rng_fwd_bwd(px, pa, noise, 0.25, 0.5, 99, 4, elem_offset=off)
+        assert g2[4] is None and torch.equal(g2[1], ga)
+
+
+def test_unlearn_step_erasediff_with_device_rng(dev):
+    """UnlearnStep(loss_fn="erasediff", device_rng=...) == the same step fed the stream's eps / t / uniform target."""
+    import copy
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.rng import DeviceRng
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.manual_seed(2)
+    net_a = torch.nn.Conv2d(1, 1, 3, padding=1).to(dev); net_b = copy.deepcopy(net_a)
+    unet = lambda net: (lambda x, t, return_dict=False, **k: (net(x.float()),))
+    B, shape = 6, (6, 1, 16, 16)
+    x0 = torch.rand(shape, device=dev) * 2 - 1; a0 = torch.rand(shape, device=dev) * 2 - 1
+    mk = lambda net, rng: UnlearnStep(unet(net), SissDDPMScheduler(), GradCombiner(net.parameters()), loss_fn="erasediff",
+                                      train_batch_size=B, eta=0.05, max_norm=1.0, device_rng=rng)
+    sa, sb = mk(net_a, DeviceRng(seed=8)), mk(net_b, None)
+    ref = DeviceRng(seed=8)
+    for it in range(2):
+        out = sa.micro_step(x0, a0)
+        ts, _ = ref.draw_rows(B, dev, t_range=(0, 1000), draw=it)
+        noise = ref.randn(shape, torch.float32, dev, draw=it)
+        target = ref.rand_aux(shape, torch.float32, dev, draw=it)
+        assert torch.equal(out["timesteps"], ts) and 0.0 <= float(target.min()) and float(target.max()) < 1.0
+        sb.micro_step(x0, a0, noise, ts, forget_target=target)
+        assert torch.equal(sa.sync_step(), sb.sync_step())
+        for p, q in zip(net_a.parameters(), net_b.parameters()):
+            assert torch.equal(p.grad, q.grad) and p.grad.abs().sum().item() > 0
