@@ -190,7 +190,7 @@ def test_ldg_kernels_pass_the_parity_suite(cuda_device):
     root = Path(__file__).resolve().parent.parent
     env = dict(os.environ, SISS_NO_TMA="1")
     cmd = [sys.executable, "-m", "pytest", str(root / "tests" / "test_kernels_gpu.py"), str(root / "tests" / "test_fuzz_gpu.py"),
-           "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+           str(root / "tests" / "test_rng_gpu.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=str(root))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout

@@ -96,3 +96,58 @@ def test_fuzz_siss_path_vs_oracle(case, cuda_device):
     dgx, dga, r1, r2 = ops.dual_mse_fwd_bwd(d(pred), d(pred * 0.5), d(nz), d(nz), go, go)
     _bits(dgx, torch.tensor(go) * (2 * (pred - nz)), "dual gx")
     _bits(dga, torch.tensor(go) * (2 * (pred * 0.5 - nz)), "dual ga")
+
+
+@pytest.mark.parametrize("case", _cases(max(N_CASES // 2, 8), seed=FUZZ_SEED + 1),
+                         ids=lambda c: f"{c[0]}-{str(c[1]).split('.')[-1]}-l{c[2]}-t{c[3]}")
+def test_fuzz_widened_kernels(case, cuda_device):
+    """The kernels of the widened rows over the same randomized shapes: device-RNG fusions == their unfused
+    compositions (bit-exact), membership kernels vs the oracle."""
+    from siss_b200 import ops
+    from siss_b200.rng import DeviceRng
+    dev = cuda_device
+    shape, dt, lambd, tmode = case
+    B = shape[0]
+    torch.manual_seed(hash(shape) % 100000 + 1)
+    ac = O.make_alphas_cumprod(); gamma, sigma = O.gamma_sigma(ac)
+    x0 = (torch.rand(shape) * 2 - 1).to(dt); a0 = (torch.rand(shape) * 2 - 1).to(dt)
+    t = [torch.randint(0, 1000, (B,)), torch.full((B,), 999), torch.randint(400, 1000, (B,))][tmode]
+    keep = torch.rand(B) > lambd
+    xd, ad, td, kd = x0.to(dev), a0.to(dev), t.to(dev), keep.to(dev)
+    per_row = x0[0].numel()
+    row_offset = int(B % 3)                          # 0, 1 or 2 rows: aligned and unaligned global offsets
+    rng = DeviceRng(seed=1000 + B, row_offset=row_offset)
+    # (1) eps generated inside K1oK2 == siss_randn then K1oK2
+    nz = rng.randn(shape, dt, dev, draw=2)
+    want = ops.add_noise_mixture(xd, ad, nz, kd, td, ac, gamma, sigma, lambd)
+    got = ops.add_noise_mixture_rng(xd, ad, kd, td, ac, gamma, sigma, lambd, rng.seed, 2, elem_offset=row_offset * per_row,
+                                    want_noise=True)
+    _bits(got[5], nz, "eps")
+    for a, b, what in zip(got[:5], want, ("x_mix", "dist_x", "dist_a", "w_x", "w_a")):
+        _bits(a, b, what)
+    # (2) EraseDiff target generated inside the dual-MSE kernel == unfused with the materialised target
+    px, pa = torch.randn(shape, device=dev), torch.randn(shape, device=dev)
+    gx, ga, rlx, rla, tgt = ops.dual_mse_rng_fwd_bwd(px, pa, nz, 0.5, 0.25, rng.seed, 2, elem_offset=row_offset * per_row,
+                                                     want_target=True)
+    assert float(tgt.min()) >= 0.0 and float(tgt.max()) < 1.0
+    rgx, rga, rrlx, rrla = ops.dual_mse_fwd_bwd(px, pa, nz.float(), tgt, 0.5, 0.25)
+    _bits(gx, rgx, "erasediff grad_x"); _bits(ga, rga, "erasediff grad_a")
+    torch.testing.assert_close(rla, rrla, rtol=1e-5, atol=1e-6)
+    # (3) membership metric: images = the batch, 3 noise draws, a ragged expanded-row slice
+    n_noise = 3
+    noise = torch.randn(n_noise, *shape[1:]).to(dt)
+    total = B * n_noise
+    r0, rows = total // 3, total - total // 3
+    ts = int(t[0])
+    xe = x0.unsqueeze(1).expand(-1, n_noise, *shape[1:]).reshape(-1, *shape[1:])
+    ae = a0.unsqueeze(1).expand(-1, n_noise, *shape[1:]).reshape(-1, *shape[1:])
+    ne = noise.unsqueeze(0).expand(B, *noise.shape).reshape(-1, *shape[1:])
+    tt = torch.full((total,), ts)
+    mx, ma = ops.membership_add_noise(xd, ad, noise.to(dev), ts, ac, r0, rows)
+    _bits(mx, O.add_noise(ac, xe, ne, tt)[r0:r0 + rows], "membership xt_x")
+    _bits(ma, O.add_noise(ac, ae, ne, tt)[r0:r0 + rows], "membership xt_a")
+    pm = torch.randn(rows, *shape[1:])
+    sx, sa = ops.membership_sqerr(pm.to(dev), (pm * 0.5).to(dev), noise.to(dev), r0)
+    nzr = ne[r0:r0 + rows].double()
+    torch.testing.assert_close(sx.cpu().double(), ((pm.double() - nzr) ** 2).flatten(1).sum(1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sa.cpu().double(), ((pm.double() * 0.5 - nzr) ** 2).flatten(1).sum(1), rtol=1e-5, atol=1e-6)

@@ -73,8 +73,8 @@ def test_draw_rows_matches_oracle_exactly(dev):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(4, 3, 256, 256), (64, 1, 28, 28), (7, 3, 33, 5), (3, 4, 64, 64), (2, 3, 512, 512)])
 def test_fused_rng_mixture_is_bitwise_randn_then_mixture(dtype, shape, dev, monkeypatch):
-    """TMA path and LDG path (SISS_NO_TMA=1 is read once per process, so the LDG path is covered by the odd-D shape
-    here and by the subprocess test in test_kernels_gpu.py's style below)."""
+    """TMA path here; the LDG path through the odd-D shape (scalar kernel) and through the SISS_NO_TMA=1 re-run of this
+    file in a subprocess (tests/test_fullsize_gpu.py::test_ldg_kernels_pass_the_parity_suite)."""
     from siss_b200 import ops
     from siss_b200.rng import DeviceRng
     B = shape[0]
