@@ -46,11 +46,11 @@ def _accumulate(net, comb, x0, a0, noise, t, keep, Bg, mode):
     loss = O.OracleDeletionLoss(*O.gamma_sigma(ac))
     all_d = {"og_latents": x0, "noisy_latents": O.add_noise(ac, x0, noise, t)}
     del_d = {"og_latents": a0, "noisy_latents": O.add_noise(ac, a0, noise, t)}
-    if mode == "siss":
+    if mode in ("siss", "shards"):
         items = loss.importance_sampling_with_mixture(net, t, noise, {}, all_d, del_d, lambd=0.5, keep_mask=keep)
     else:
         items = loss.naive_del(net, t, noise, {}, all_d, del_d)
-    if mode == "siss":
+    if mode in ("siss", "shards"):
         comb.begin_x(); (items[5].sum() / Bg).backward(retain_graph=True)
         comb.begin_a(); (items[6].sum() / Bg).backward()
     else:
@@ -76,6 +76,17 @@ def _worker(rank, world, port, mode, q):
     keep = parallel.global_keep_mask(Bg, 0.5, rank, world)
     sh = lambda v: parallel.shard_rows(v, rank, world)
     _accumulate(net, comb, sh(x0), sh(a0), sh(noise), sh(t), keep, Bg, mode)
+    if mode == "shards":
+        # first half of the exchange only (what the ZeRO-1 optimiser step continues from): reduced shards + global sums
+        sums = comb.reduce_to_shards()
+        full_x, full_a = torch.empty(comb.total), torch.empty(comb.total)
+        dist.all_gather_into_tensor(full_x, comb._shard_x)
+        dist.all_gather_into_tensor(full_a, comb._shard_a)
+        if rank == 0:
+            q.put((torch.cat([full_x, full_a]), sums.clone()))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     stats = comb.combine(scaling_norm=5.0, max_norm=1.0) if mode == "siss" else comb.clip_only(1.0)
     flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     gathered = [torch.empty_like(flat) for _ in range(world)]
@@ -125,7 +136,7 @@ def test_two_rank_combine_equals_single_rank(mode):
     all_d = {"og_latents": x0, "noisy_latents": O.add_noise(ac, x0, noise, t)}
     del_d = {"og_latents": a0, "noisy_latents": O.add_noise(ac, a0, noise, t)}
     loop = O.ReferenceGradLoop(ref_net, train_batch_size=Bg)
-    if mode == "siss":
+    if mode in ("siss", "shards"):
         items = loss.importance_sampling_with_mixture(ref_net, t, noise, {}, all_d, del_d, lambd=0.5, keep_mask=keep)
         loop.micro_step(items, retain_graph=True)
         loop.sync_step(False, scaling_norm=5.0, max_norm=1.0)
@@ -163,3 +174,36 @@ def test_combine_stand_in_matches_flat_oracle():
         out, _ = O.combine_from_sums_cpu(gx, ga, O.norm3_cpu(gx, ga), mode, val, 1.0, stats=stats)
         torch.testing.assert_close(out, exp, rtol=2e-5, atol=1e-8)
         torch.testing.assert_close(stats, torch.stack([nx, na, s.float(), tn, clip.float()]), rtol=2e-5, atol=1e-7)
+
+
+def test_two_rank_reduce_to_shards():
+    """GradCombiner.reduce_to_shards (the exchange half the sharded optimiser step starts from): the gathered shards are
+    the rank-summed G_x / G_a of the 1-rank run on the concatenated batch, and sums3 are their global sums."""
+    from oracle import siss_oracle as O
+    from siss_b200 import parallel
+    from siss_b200.grad_combine import GradCombiner
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 200) + 7
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, "shards", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full2, sums2 = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Bg = 6
+    net = TinyNet()
+    comb = GradCombiner(net.parameters(), distributed=False)
+    x0, a0, noise, t = _make_batch(Bg)
+    torch.manual_seed(9)
+    keep = parallel.global_keep_mask(Bg, 0.5, 0, 1)
+    _accumulate(net, comb, x0, a0, noise, t, keep, Bg, "shards")
+    n = comb.total
+    pad = full2.numel() // 2 - n                         # the 2-rank buffers are padded to a multiple of 4 * world
+    assert pad >= 0 and full2[n:n + pad].abs().sum() == 0
+    torch.testing.assert_close(full2[:n], comb.g_x, rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(full2[n + pad:2 * n + pad], comb.g_a, rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(sums2, O.norm3_cpu(comb.g_x, comb.g_a), rtol=1e-5, atol=0)
+    with pytest.raises(RuntimeError):
+        comb.reduce_to_shards()                          # a data-parallel step: refuses on a single rank
