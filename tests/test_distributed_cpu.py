@@ -99,15 +99,16 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("mode", ["siss", "naive"])
-def test_two_rank_combine_equals_single_rank(mode):
+def test_n_rank_combine_equals_single_rank(mode, world):
     from oracle import siss_oracle as O
     from siss_b200 import parallel
     from siss_b200.grad_combine import GradCombiner
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 200) + (0 if mode == "siss" else 1)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 200) + (0 if mode == "siss" else 1) + 10 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
     flat2, stats2 = q.get(timeout=180)
