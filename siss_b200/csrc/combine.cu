@@ -14,6 +14,8 @@
 
 namespace siss {
 
+int env_int(const char* name, int dflt);
+
 int cached_sm_count();
 
 constexpr int kK4Occ = 4;     // resident CTAs per SM the kernels are compiled for
@@ -36,14 +38,19 @@ inline Norm3Workspace carve_norm3(void* ws) {
 
 __global__ void __launch_bounds__(kThreads, kK4Occ)
 norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long long n, long long nvec,
-             double* __restrict__ sums3, Norm3Workspace ws) {
+             double* __restrict__ sums3, Norm3Workspace ws, long long keep_from_vec) {
     __shared__ double red[3 * kWarps];
     __shared__ int flag;
     double acc[3] = {0.0, 0.0, 0.0};
+    // The combine that follows walks the buffers in REVERSE, so the tail [keep_from_vec, nvec) of both buffers is what
+    // it reads first: load it with L2 evict_last priority and everything before it as read-once (evict_first), so the
+    // tail is still L2-resident when the combine starts (instead of whatever the default replacement leaves).
+    const unsigned long long pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
 
     const long long nchunks = (nvec + kK4Chunk - 1) / kK4Chunk;
     for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const long long base = c * kK4Chunk + threadIdx.x;
+        const unsigned long long pol = (c * kK4Chunk >= keep_from_vec) ? pol_keep : pol_once;   // uniform per chunk
         uint4 rx[kK4Unroll], ra[kK4Unroll];
         bool ok[kK4Unroll];
 #pragma unroll
@@ -51,8 +58,8 @@ norm3_kernel(const float* __restrict__ gx, const float* __restrict__ ga, long lo
             const long long i = base + (long long)j * kThreads;
             ok[j] = i < nvec;
             if (ok[j]) {
-                rx[j] = ldg_stream(gx + 4 * i);
-                ra[j] = ldg_stream(ga + 4 * i);
+                rx[j] = ldg_stream_hint(gx + 4 * i, pol);
+                ra[j] = ldg_stream_hint(ga + 4 * i, pol);
             }
         }
         // Products and sums in fp64 (exact products of fp32 values): the clip needs
@@ -185,7 +192,12 @@ int siss_norm3(const float* g_x, const float* g_a, int64_t n, double* sums3, voi
     if (!g_x || !g_a || !sums3 || !workspace || n < 0) return SISS_EINVAL;
     const long long nvec = (aligned16(g_x) && aligned16(g_a)) ? n / 4 : 0;
     Norm3Workspace ws = carve_norm3(workspace);
-    norm3_kernel<<<k4_grid(nvec, n), kThreads, 0, (cudaStream_t)stream>>>(g_x, g_a, n, nvec, sums3, ws);
+    // bytes of (both) buffers' tails to keep in the 126 MB L2 for the combine; 0 disables the hints' effect
+    static const long long keep_mb = env_int("SISS_L2_KEEP_MB", 80);
+    long long keep_vec = (keep_mb << 20) / 2 / 16;
+    if (g_a == g_x) keep_vec *= 2;                                   // single-term: one buffer, all of the budget
+    const long long keep_from = (keep_mb <= 0) ? nvec : (nvec > keep_vec ? nvec - keep_vec : 0);
+    norm3_kernel<<<k4_grid(nvec, n), kThreads, 0, (cudaStream_t)stream>>>(g_x, g_a, n, nvec, sums3, ws, keep_from);
     return (int)cudaGetLastError();
 }
 

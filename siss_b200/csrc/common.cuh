@@ -31,6 +31,26 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     return r;
 }
 
+// L2 eviction-priority policies for loads whose data a FOLLOWING kernel re-reads (K4a's tail, consumed first by K4b's
+// reverse walk): `evict_last` lines are the last candidates for replacement, `evict_first` marks read-once data.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg_stream_hint(const void* p, unsigned long long policy) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+
 // plain (coherent) 128-bit load: for buffers another kernel may still be L2-resident for
 __device__ __forceinline__ uint4 ldg_v4(const void* p) {
     uint4 r;
