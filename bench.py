@@ -704,7 +704,11 @@ def run_siss(args):
                                  "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/; "
                                  "copy_same_bytes_ms = a plain D2D copy moving the kernel's algorithmic bytes under the same "
                                  "bracket with L2 flushed (the floor at that size), vs_copy_same_bytes = that / kernel ms"),
-                "kernel_share_of_step": sum(kernel_ms.values()) / (elapsed_ms / args.steps)}
+                "kernel_share_of_step": sum(kernel_ms.values()) / (elapsed_ms / args.steps),
+                "l2_note": ("siss_combine re-reads what siss_norm3 just streamed; siss_norm3 leaves the last SISS_L2_KEEP_MB "
+                            "(default 80) MB of the buffers in L2 with an evict_last policy and the combine walks in reverse, so "
+                            "~6 % of its algorithmic bytes never reach DRAM and frac may exceed 1. `traffic` is an ncu capture, "
+                            "which flushes caches before the profiled kernel and therefore cannot show that reuse")}
 
     # ---------------------------------------------------------------- e2e arm (public API, host buffers)
     e2e = None
