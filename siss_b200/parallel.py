@@ -15,7 +15,7 @@ NegGrad term is never reduced) and is deliberately not reproduced
 from __future__ import annotations
 
 import os
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist

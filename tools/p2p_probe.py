@@ -2,7 +2,6 @@
 """torchrun probe: time the pieces of the fused NVLink exchange (barrier, reduce-scatter+K4a kernel,
 K4b+all-gather kernel) separately. Usage: torchrun --nproc-per-node N tools/p2p_probe.py [P]"""
 import ctypes
-import os
 import sys
 from pathlib import Path
 
