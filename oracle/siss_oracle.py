@@ -19,11 +19,19 @@ promotion and bf16 rounding are the reference's), of
 Parity pinning:
   * loss class: PINNED — tests/golden/*.npz are outputs of the reference's own file executed from
     /root/reference by tests/golden/make_golden.py; tests/test_oracle_golden.py checks this module
-    against them bit for bit.
-  * add_noise, accelerate.backward scaling, combine block: the reference holds no test, fixture or
-    golden vector for them and their third-party halves are absent: PARITY UNPINNED at that
-    boundary. The combine restatement is additionally cross-checked against real autograd on a
-    small module (tests/test_oracle_golden.py::test_combine_matches_literal_loop).
+    against them bit for bit. Where the reference checkout exists (the build container),
+    tests/test_oracle_vs_reference_live.py also compares against the imported reference class on
+    randomized cases (outputs and gradients, bit-exact).
+  * combine block (``ReferenceGradLoop``): PINNED in the build container — the same live test reads the
+    block's own source lines from delete_celeb.py / delete_tshirt.py / delete_sd.py, executes them with
+    stub ``accelerator`` / ``cfg`` / ``wandb`` objects and compares gradients and logged scalars bit for
+    bit. It is also cross-checked against real autograd on a small module
+    (tests/test_oracle_golden.py::test_combine_matches_literal_loop).
+  * membership metric: PINNED (tests/golden/membership_*.npz from the reference class + the live test).
+  * add_noise / beta schedules (diffusers), ``accelerator.backward`` scaling and ``clip_grad_norm_``
+    routing (accelerate), EMAModel (diffusers): third-party packages that are neither vendored by the
+    reference nor installed here — restated from their published behaviour, PARITY UNPINNED at that
+    boundary (the reference holds no test, fixture or golden vector for them).
 
 Every function is dtype-generic: call it with float64 tensors to get the "exact" answer the fp32
 results are compared against.
