@@ -80,10 +80,12 @@ def hot_path_params(cfg: Dict[str, Any]) -> Dict[str, Any]:
 
 
 def step_from_config(cfg: Dict[str, Any], unet, scheduler, combiner, max_norm: float = 1.0,
-                     inf_guard: bool = False):
+                     inf_guard: bool = False, superfactor_decay_on: str = "micro_step"):
     """UnlearnStep with the config's meaning: ``scaling_norm`` applies to SISS / No-IS, ``eta`` to EraseDiff
     (delete_celeb.py:740-746), ``lambd`` / ``superfactor`` are the method kwargs (``**loss_params``, :622),
-    the loss is divided by ``train_batch_size`` and by ``gradient_accumulation_steps`` (:686-691)."""
+    the loss is divided by ``train_batch_size`` and by ``gradient_accumulation_steps`` (:686-691).
+    ``superfactor_decay_on``: "micro_step" is what delete_celeb.py / delete_tshirt.py do with ``deletion.superfactor_decay``,
+    "sync_step" what delete_sd.py does (once per optimiser step, delete_sd.py:1173-1193)."""
     from .step import UnlearnStep
     hp = hot_path_params(cfg)
     fn = hp["loss_fn"]
@@ -93,7 +95,7 @@ def step_from_config(cfg: Dict[str, Any], unet, scheduler, combiner, max_norm: f
                        scaling_norm=hp["scaling_norm"] if fn in ("importance_sampling_with_mixture",
                                                                  "double_forward_with_neg_del") else None,
                        eta=hp["eta"] if fn == "erasediff" else None, max_norm=max_norm, inf_guard=inf_guard,
-                       superfactor_decay=hp["superfactor_decay"])
+                       superfactor_decay=hp["superfactor_decay"], superfactor_decay_on=superfactor_decay_on)
 
 
 def adamw_kwargs(cfg: Dict[str, Any]) -> Dict[str, Any]:

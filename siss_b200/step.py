@@ -48,13 +48,15 @@ class UnlearnStep:
                  superfactor: Optional[float] = None, scaling_norm: Optional[float] = None,
                  eta: Optional[float] = None, max_norm: Optional[float] = 1.0, inf_guard: bool = False,
                  superfactor_decay: Optional[float] = None, device_rng=None,
-                 t_range: Optional[Tuple[int, int]] = None):
+                 t_range: Optional[Tuple[int, int]] = None, superfactor_decay_on: str = "micro_step"):
         """``device_rng`` (a :class:`siss_b200.rng.DeviceRng`, opt-in): draw eps, the timesteps and the Bernoulli mask
         on the device from the counter-based stream whenever ``micro_step`` is not given them — for SISS eps is then
         generated inside K1oK2 and never touches HBM. ``t_range`` = [lo, hi) for drawn timesteps (default: the whole
         schedule, delete_tshirt.py:535-540; (999, 1000) reproduces delete_celeb.py:593-598)."""
         if loss_fn not in TWO_TERM + ONE_TERM:
             raise ValueError(f"unknown loss_fn {loss_fn!r}")
+        if superfactor_decay_on not in ("micro_step", "sync_step"):
+            raise ValueError('superfactor_decay_on must be "micro_step" or "sync_step"')
         if loss_fn == "importance_sampling_with_mixture" and lambd is None:
             raise ValueError("importance_sampling_with_mixture needs lambd")
         if loss_fn == "simple_neg_del" and superfactor is None:
@@ -71,6 +73,9 @@ class UnlearnStep:
         # `deletion.superfactor_decay`: the reference multiplies loss_params.superfactor by it after every
         # micro-step's statistics (delete_celeb.py:658-662), i.e. the NEXT micro-step sees the decayed value
         self.superfactor_decay = superfactor_decay
+        # ... in delete_celeb.py / delete_tshirt.py (:600-604). delete_sd.py applies the decay once per OPTIMISER step
+        # instead, under `if accelerator.sync_gradients:` (delete_sd.py:1173-1193): superfactor_decay_on="sync_step".
+        self.superfactor_decay_on = superfactor_decay_on
         self.scaling_norm, self.eta, self.max_norm, self.inf_guard = scaling_norm, eta, max_norm, inf_guard
         self.go = upstream_scale(self.train_batch_size, self.G)
         dev = combiner.device
@@ -168,18 +173,26 @@ class UnlearnStep:
             cb.begin_x()
             torch.autograd.backward(pred, g)
             out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl
-        if self.superfactor is not None and self.superfactor_decay is not None:
+        if self.superfactor is not None and self.superfactor_decay is not None and self.superfactor_decay_on == "micro_step":
             self.superfactor *= self.superfactor_decay
         if draw is not None:
             rng.advance()                  # next micro-step draws from the next index (host mirror + device counter)
         self._micro += 1
         return out
 
+    def end_of_optimizer_step(self) -> None:
+        """Bookkeeping at the accumulation boundary: restart the micro-step count and, for
+        ``superfactor_decay_on="sync_step"``, apply the decay (delete_sd.py:1190-1193). ``sync_step`` calls it; call it
+        yourself when the boundary is handled by ``FusedCombineAdamW.step`` instead."""
+        self._micro = 0
+        if self.superfactor is not None and self.superfactor_decay is not None and self.superfactor_decay_on == "sync_step":
+            self.superfactor *= self.superfactor_decay
+
     def sync_step(self) -> torch.Tensor:
         """Gradient combine + clip at the accumulation boundary (delete_celeb.py:714-767). Leaves
         ``param.grad`` ready for ``optimizer.step()``; returns the device stats tensor
         ``[norm_loss_x, norm_loss_a, scaling_factor, total_norm, clip_coef]``."""
-        self._micro = 0
+        self.end_of_optimizer_step()
         if self.loss_fn in ONE_TERM:
             return self.combiner.clip_only(self.max_norm if self.max_norm is not None else 0.0)
         if self.loss_fn == "erasediff":

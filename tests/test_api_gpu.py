@@ -323,6 +323,45 @@ def test_fused_combine_adamw_matches_reference_loop_plus_torch_adamw(loss_fn, kw
             torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=3e-5, atol=3e-6)
 
 
+@pytest.mark.parametrize("decay_on", ["micro_step", "sync_step"])
+def test_superfactor_decay_schedules(decay_on, dev):
+    """`deletion.superfactor_decay`: delete_celeb.py / delete_tshirt.py multiply loss_params.superfactor after every
+    micro-step's statistics (:658-662), delete_sd.py once per optimiser step (delete_sd.py:1173-1193). Two optimiser steps
+    of G = 2 with NegGrad against the reference loop fed the superfactor sequence of the respective task file."""
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep
+    torch.backends.cudnn.allow_tf32 = False
+    B, G, s0, d = 4, 2, 0.8, 0.5
+    cpu_net = TinyNet(); gpu_net = copy.deepcopy(cpu_net).to(dev)
+    sched = SissDDPMScheduler()
+    oloss = O.OracleDeletionLoss(*O.gamma_sigma(sched.alphas_cumprod))
+    loop = O.ReferenceGradLoop(cpu_net, train_batch_size=B, grad_accum_steps=G)
+    comb = GradCombiner(gpu_net.parameters())
+    step = UnlearnStep(gpu_net, sched, comb, loss_fn="simple_neg_del", train_batch_size=B, gradient_accumulation_steps=G,
+                       superfactor=s0, superfactor_decay=d, superfactor_decay_on=decay_on, max_norm=1.0)
+    want_sf = [s0, s0 * d, s0 * d * d, s0 * d ** 3] if decay_on == "micro_step" else [s0, s0, s0 * d, s0 * d]
+    torch.manual_seed(4)
+    for it in range(2):
+        for k in range(G):
+            sf = want_sf[it * G + k]
+            assert step.superfactor == pytest.approx(sf)
+            x0, a0 = torch.rand(B, 1, 8, 8) * 2 - 1, torch.rand(B, 1, 8, 8) * 2 - 1
+            noise, t = torch.randn(B, 1, 8, 8), torch.randint(300, 1000, (B,))
+            all_d = {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)}
+            del_d = {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}
+            loop.micro_step(oloss.simple_neg_del(cpu_net, t, noise, {}, all_d, del_d, superfactor=sf), retain_graph=False)
+            step.micro_step(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev))
+        loop.sync_step(True, "simple_neg_del", max_norm=1.0)
+        step.sync_step()
+        for p, q in zip(gpu_net.parameters(), cpu_net.parameters()):
+            torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-4, atol=2e-6)
+        for q in cpu_net.parameters():
+            q.grad = None
+    with pytest.raises(ValueError):
+        UnlearnStep(gpu_net, sched, comb, loss_fn="naive_del", train_batch_size=B, superfactor_decay_on="epoch")
+
+
 def test_grad_combiner_after_spelling_equals_begin_spelling(dev):
     """SURVEY §8b sketches the combine boundary as after_backward_x / after_backward_a / combine(mode, value); both
     spellings must drive the same kernels to bit-identical gradients over 2 optimiser steps x 2 micro-steps."""

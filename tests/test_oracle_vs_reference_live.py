@@ -245,3 +245,64 @@ def test_reference_grad_loop_equals_the_reference_source_block(task, loss_fn, G)
         assert float(logged[0]["gradient/scaling_factor"]) == float(out["scaling_factor"])
     else:
         assert logged == []
+
+
+def _stats_block(path: Path):
+    """`batch_stats = {}` ... `wandb.log(batch_stats, step=...)` of run() (delete_celeb.py:626-663 and twins), compiled
+    from the reference's source text as a function body."""
+    import textwrap
+    lines = path.read_text().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.strip() == "batch_stats = {}")
+    end = next(i for i in range(start, len(lines)) if lines[i].strip().startswith("wandb.log(batch_stats"))
+    body = textwrap.dedent("\n".join(lines[start:end + 1]))
+    src = ("def block(self, wandb, global_step, loss, loss_x, loss_a, importance_weight_x, importance_weight_a, print):\n"
+           + textwrap.indent(body, "    ") + "\n    return batch_stats\n")
+    ns = {"img_count": 0}
+    exec(compile(src, f"<statistics block of {path.name}>", "exec"), ns)
+    return ns["block"]
+
+
+@pytest.mark.skipif(not all(p.is_file() for p in TASKS.values()), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("task", list(TASKS))
+@pytest.mark.parametrize("loss_fn", ["importance_sampling_with_mixture", "double_forward_with_neg_del", "simple_neg_del",
+                                     "naive_del"])
+def test_batch_stats_restatement_equals_the_reference_source_block(task, loss_fn):
+    """oracle.batch_stats (what the fused statistics kernel is compared with) vs the reference's own logging block,
+    executed from source; also the superfactor decay the block applies (`deletion.superfactor_decay`)."""
+    from types import SimpleNamespace
+
+    class Params(dict):                                      # OmegaConf-like: `"superfactor" in p` and `p.superfactor`
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    block = _stats_block(TASKS[task])
+    B = 6
+    ac = O.make_alphas_cumprod(); gamma, sigma = O.gamma_sigma(ac)
+    torch.manual_seed(3)
+    x0, a0 = torch.rand(B, 3, 8, 8) * 2 - 1, torch.rand(B, 3, 8, 8) * 2 - 1
+    noise, t = torch.randn(B, 3, 8, 8), torch.randint(200, 1000, (B,))
+    all_d = {"og_latents": x0, "noisy_latents": O.add_noise(ac, x0, noise, t)}
+    del_d = {"og_latents": a0, "noisy_latents": O.add_noise(ac, a0, noise, t)}
+    kwargs = dict(lambd=0.5) if loss_fn.startswith("importance") else (dict(superfactor=2.0) if loss_fn == "simple_neg_del" else {})
+    items = getattr(O.OracleDeletionLoss(gamma, sigma), loss_fn)(_Stub(), t, noise, {}, all_d, del_d, **kwargs)
+    params = Params(kwargs)
+    cfg = SimpleNamespace(deletion=SimpleNamespace(loss_params=params, superfactor_decay=0.9))
+    logged = []
+    wandb = SimpleNamespace(log=lambda d, step=None: logged.append(dict(d)))
+    got = block(SimpleNamespace(cfg=cfg), wandb, 0, *items[:5], lambda *a, **k: None)
+    want = O.batch_stats(items)
+    ref_stats = {k: v for k, v in got.items() if k != "superfactor"}
+    assert set(ref_stats) == set(want) and len(logged) == 1
+    for k in want:
+        assert ref_stats[k] == want[k] or (np.isnan(ref_stats[k]) and np.isnan(want[k])), k
+    if loss_fn == "simple_neg_del" and task != "delete_sd":
+        assert got["superfactor"] == 2.0 and params.superfactor == pytest.approx(1.8)     # decayed for the NEXT micro-step
+    if task == "delete_sd":
+        # delete_sd.py decays once per OPTIMISER step instead (under `if accelerator.sync_gradients:`, :1173-1193):
+        # UnlearnStep(superfactor_decay_on="sync_step")
+        assert "superfactor" not in got and params.get("superfactor", 2.0) == 2.0
+        src = TASKS[task].read_text().splitlines()
+        i_sync = max(i for i, l in enumerate(src[:1193]) if l.strip() == "if accelerator.sync_gradients:")
+        i_dec = next(i for i, l in enumerate(src) if "loss_params.superfactor *= self.cfg.deletion.superfactor_decay" in l)
+        indent = lambda l: len(l) - len(l.lstrip())
+        assert i_sync < i_dec and all(indent(l) > indent(src[i_sync]) for l in src[i_sync + 1:i_dec + 1] if l.strip())
