@@ -142,3 +142,36 @@ def test_argument_validation_without_a_gpu():
     assert lib.siss_mt_norm3(one, one, one, one, 0, 1, one, one, N) == -1                # no tensors
     for code in (-1, -2, -3):
         assert _lib.error_string(code).startswith("siss:")
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/siss_b200.h must compile as strict C99 (and as C++), with no CUDA or
+    torch headers, and a C program must link against libsiss_b200.so and call an entry point that needs no GPU."""
+    import shutil
+    import subprocess
+    hdr = ROOT / "include" / "siss_b200.h"
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", str(hdr)], check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", str(hdr)], check=True)
+    txt = hdr.read_text()
+    includes = [l.split()[1] for l in txt.splitlines() if l.startswith("#include")]
+    assert set(includes) <= {"<stdint.h>", "<stddef.h>"}, includes            # no CUDA, no torch headers in the boundary
+    from siss_b200 import _lib
+    _lib.load()                                                   # builds the library if it is missing
+    src = tmp_path / "main.c"
+    src.write_text('#include <stdio.h>\n#include "siss_b200.h"\n'
+                   'int main(void) {\n'
+                   '  printf("%d %s|%lld\\n", siss_abi_version(), siss_error_string(SISS_EINVAL),\n'
+                   '         (long long)siss_row_workspace_bytes(64));\n'
+                   '  return siss_add_noise(0, 0, 0, 0, 1000, 0, 1, 1, SISS_F32, 0) == SISS_EINVAL ? 0 : 1;\n}\n')
+    exe = tmp_path / "main"
+    libdir = _lib.LIB_PATH.parent
+    subprocess.run([gcc, "-std=c99", "-I", str(hdr.parent), str(src), "-o", str(exe), f"-L{libdir}", "-lsiss_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    ver, rest = out.split(" ", 1)
+    assert int(ver) == _lib.ABI_VERSION and "invalid argument" in rest and int(rest.rsplit("|", 1)[1]) > 0
