@@ -25,7 +25,9 @@ Parity pinning:
   * combine block (``ReferenceGradLoop``): PINNED in the build container — the same live test reads the
     block's own source lines from delete_celeb.py / delete_tshirt.py / delete_sd.py, executes them with
     stub ``accelerator`` / ``cfg`` / ``wandb`` objects and compares gradients and logged scalars bit for
-    bit. It is also cross-checked against real autograd on a small module
+    bit; tests/golden/step_*.npz (whole optimiser steps produced by the reference's loss class and that block
+    together, tests/golden/make_golden_step.py) carry the pin to the GPU box (tests/test_step_golden.py).
+    It is also cross-checked against real autograd on a small module
     (tests/test_oracle_golden.py::test_combine_matches_literal_loop).
   * membership metric: PINNED (tests/golden/membership_*.npz from the reference class + the live test).
   * add_noise / beta schedules (diffusers), ``accelerator.backward`` scaling and ``clip_grad_norm_``

@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
-GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz") if not p.stem.startswith("membership_"))
+GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz") if not p.stem.startswith(("membership_", "step_")))
+STEP_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("step_*.npz"))               # make_golden_step.py
 MEMBERSHIP_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("membership_*.npz"))   # make_golden_membership.py
 
 
@@ -63,3 +64,19 @@ def weight_tolerance(d_x: torch.Tensor, d_a: torch.Tensor, k: float = 8.0) -> to
     noise: |delta(d_x - d_a)| <= k * eps32 * (d_x + d_a); d(log w) <= |delta|. Plus 1e-5 floor."""
     eps = torch.finfo(torch.float32).eps
     return k * eps * (d_x.abs() + d_a.abs()).double() + 1e-5
+
+
+
+class GoldenStepNet(torch.nn.Module):
+    """The small UNet stand-in the step_*.npz fixtures were generated with (make_golden_step.py); its initial parameters
+    are stored in the fixtures, so only the architecture has to match."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(5)
+        self.c1 = torch.nn.Conv2d(1, 4, 3, padding=1)
+        self.c2 = torch.nn.Conv2d(4, 1, 3, padding=1)
+        self.odd = torch.nn.Parameter(torch.full((3,), 0.01))
+
+    def forward(self, x, timesteps, return_dict=False, **kw):
+        return (self.c2(torch.tanh(self.c1(x))) + self.odd.sum() + timesteps.reshape(-1, 1, 1, 1).float() * 1e-4,)
