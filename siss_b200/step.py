@@ -96,89 +96,109 @@ class UnlearnStep:
         of ddpm_deletion_loss.py:75 with a given tensor — for reproducible tests and replays."""
         cond = conditioning or {}
         out: Dict[str, torch.Tensor] = {}
-        cb = self.combiner
         last = self._micro == self.G - 1          # last accumulation micro-step of this optimiser step
-        rng, draw = self.device_rng, None
         siss = self.loss_fn == "importance_sampling_with_mixture"
-        if noise is None or timesteps is None:
-            if rng is None:
-                raise ValueError("noise= and timesteps= are required unless the step was built with device_rng=")
-            draw = rng.next_draw()         # an explicit draw= below would bypass the device-side counter: pass None
-            if timesteps is None or (siss and keep_mask is None):
-                ts_d, keep_d = rng.draw_rows(x0.shape[0], x0.device, t_range=self.t_range if timesteps is None else None,
-                                             lambd=self.lambd if (siss and keep_mask is None) else None)
-                timesteps = ts_d if timesteps is None else timesteps
-                keep_mask = keep_d if keep_d is not None else keep_mask
-            if noise is None and not siss:
-                noise = rng.randn(x0.shape, x0.dtype, x0.device)
-            out["timesteps"] = timesteps
+        noise, timesteps, keep_mask, draw = self._device_draws(x0, noise, timesteps, keep_mask, siss, out)
         if siss:
-            keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
-            if noise is None:     # eps generated inside K1oK2 (registers only)
-                per_row = x0.numel() // max(x0.shape[0], 1)
-                x_mix, d_x, d_a, w_x, w_a, _ = ops.add_noise_mixture_rng(
-                    x0, a0, keep, timesteps, self.alphas_cumprod, self.gamma, self.sigma, self.lambd, rng.seed, draw,
-                    elem_offset=rng.row_offset * per_row, d_draw=rng.d_draw)
-            else:
-                x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
-                                                                  self.gamma, self.sigma, self.lambd)
-            pred = self.unet(x_mix, timesteps, **cond, return_dict=False)[0]
-            g_x, g_a, rl_x, rl_a = ops.wmse_fwd_bwd(pred.detach(), x_mix, x0, a0, timesteps, self.gamma, self.sigma,
-                                                    w_x, w_a, self.go, self.go)
-            cb.begin_x()
-            torch.autograd.backward(pred, g_x, retain_graph=True)
-            cb.begin_a(last_micro_step=last)      # data parallel: G_x's reduce-scatter overlaps backward #2
-            torch.autograd.backward(pred, g_a)
-            out.update(w_x=w_x, w_a=w_a, dist_x=d_x, dist_a=d_a, row_loss_x=rl_x, row_loss_a=rl_a)
+            self._micro_siss(x0, a0, noise, timesteps, keep_mask, cond, draw, last, out)
         elif self.loss_fn in ("double_forward_with_neg_del", "erasediff"):
-            xt_x, xt_a = self.scheduler.add_noise_pair(x0, a0, noise, timesteps)
-            pred_x = self.unet(xt_x, timesteps, **cond, return_dict=False)[0]
-            pred_a = self.unet(xt_a, timesteps, **cond, return_dict=False)[0]
-            # EraseDiff's forget target: uniform noise drawn after the second forward (ddpm_deletion_loss.py:75)
-            if self.loss_fn == "erasediff" and forget_target is None and rng is not None:
-                # opt-in device RNG: the uniform target is drawn inside the kernel (aux domain of this micro-step's draw)
-                if draw is None:
-                    draw = rng.next_draw()
-                per_row = x0.numel() // max(x0.shape[0], 1)
-                g_x, g_a, rl_x, rl_a, _ = ops.dual_mse_rng_fwd_bwd(
-                    pred_x.detach(), pred_a.detach(), noise, self.go, self.go, rng.seed, draw,
-                    elem_offset=rng.row_offset * per_row, d_draw=rng.d_draw)
-            else:
-                if self.loss_fn == "erasediff":
-                    tgt_a = torch.rand_like(pred_a) if forget_target is None else forget_target
-                else:
-                    tgt_a = noise
-                tgt_x = noise
-                if tgt_a.dtype != tgt_x.dtype:
-                    tgt_x = tgt_x.to(tgt_a.dtype)
-                g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a,
-                                                            self.go, self.go)
-            cb.begin_x()
-            torch.autograd.backward(pred_x, g_x)
-            cb.begin_a(last_micro_step=last)
-            torch.autograd.backward(pred_a, g_a)
-            out.update(row_loss_x=rl_x, row_loss_a=rl_a)
+            draw = self._micro_two_forward(x0, a0, noise, timesteps, forget_target, cond, draw, last, out)
         else:
-            # single-term methods: one forward, one backward, no combine (delete_celeb.py:682-684)
-            if self.loss_fn == "naive_del":
-                xt = self.scheduler.add_noise(x0, noise, timesteps)
-                alpha = 1.0
-            else:
-                xt = self.scheduler.add_noise(a0, noise, timesteps)
-                alpha = -float(self.superfactor)
-            pred = self.unet(xt, timesteps, **cond, return_dict=False)[0]
-            # grad = (go * alpha) * 2 (pred - eps): dual kernel with the second term switched off
-            g, _unused, rl, _ = ops.dual_mse_fwd_bwd(pred.detach(), pred.detach(), noise, noise,
-                                                     float(np.float32(self.go) * np.float32(alpha)), 0.0)
-            cb.begin_x()
-            torch.autograd.backward(pred, g)
-            out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl
+            self._micro_single_term(x0, a0, noise, timesteps, cond, out)
         if self.superfactor is not None and self.superfactor_decay is not None and self.superfactor_decay_on == "micro_step":
             self.superfactor *= self.superfactor_decay
         if draw is not None:
-            rng.advance()                  # next micro-step draws from the next index (host mirror + device counter)
+            self.device_rng.advance()      # next micro-step draws from the next index (host mirror + device counter)
         self._micro += 1
         return out
+
+    def _device_draws(self, x0, noise, timesteps, keep_mask, siss: bool, out: Dict[str, torch.Tensor]):
+        """Opt-in device RNG: fill in whatever of (timesteps, keep mask, eps) the caller left out. For SISS eps stays
+        None — it is generated inside K1oK2. Returns (noise, timesteps, keep_mask, draw index or None)."""
+        if noise is not None and timesteps is not None:
+            return noise, timesteps, keep_mask, None
+        rng = self.device_rng
+        if rng is None:
+            raise ValueError("noise= and timesteps= are required unless the step was built with device_rng=")
+        draw = rng.next_draw()             # the calls below pass no draw=: that would bypass the device-side counter
+        if timesteps is None or (siss and keep_mask is None):
+            ts_d, keep_d = rng.draw_rows(x0.shape[0], x0.device, t_range=self.t_range if timesteps is None else None,
+                                         lambd=self.lambd if (siss and keep_mask is None) else None)
+            timesteps = ts_d if timesteps is None else timesteps
+            keep_mask = keep_d if keep_d is not None else keep_mask
+        if noise is None and not siss:
+            noise = rng.randn(x0.shape, x0.dtype, x0.device)
+        out["timesteps"] = timesteps
+        return noise, timesteps, keep_mask, draw
+
+    def _micro_siss(self, x0, a0, noise, timesteps, keep_mask, cond, draw, last: bool, out) -> None:
+        """importance_sampling_with_mixture: K1oK2 -> UNet -> K3 -> two backward passes from one forward."""
+        cb, rng = self.combiner, self.device_rng
+        keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
+        if noise is None:     # eps generated inside K1oK2 (registers only)
+            per_row = x0.numel() // max(x0.shape[0], 1)
+            x_mix, d_x, d_a, w_x, w_a, _ = ops.add_noise_mixture_rng(
+                x0, a0, keep, timesteps, self.alphas_cumprod, self.gamma, self.sigma, self.lambd, rng.seed, draw,
+                elem_offset=rng.row_offset * per_row, d_draw=rng.d_draw)
+        else:
+            x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
+                                                              self.gamma, self.sigma, self.lambd)
+        pred = self.unet(x_mix, timesteps, **cond, return_dict=False)[0]
+        g_x, g_a, rl_x, rl_a = ops.wmse_fwd_bwd(pred.detach(), x_mix, x0, a0, timesteps, self.gamma, self.sigma,
+                                                w_x, w_a, self.go, self.go)
+        cb.begin_x()
+        torch.autograd.backward(pred, g_x, retain_graph=True)
+        cb.begin_a(last_micro_step=last)      # data parallel: G_x's reduce-scatter overlaps backward #2
+        torch.autograd.backward(pred, g_a)
+        out.update(w_x=w_x, w_a=w_a, dist_x=d_x, dist_a=d_a, row_loss_x=rl_x, row_loss_a=rl_a)
+
+    def _micro_two_forward(self, x0, a0, noise, timesteps, forget_target, cond, draw, last: bool, out):
+        """double_forward_with_neg_del / erasediff: K1 pair -> two UNet forwards -> dual-MSE kernel -> two backward passes.
+        Returns the draw index used (EraseDiff with the device RNG takes one even when eps and t were given)."""
+        cb, rng = self.combiner, self.device_rng
+        xt_x, xt_a = self.scheduler.add_noise_pair(x0, a0, noise, timesteps)
+        pred_x = self.unet(xt_x, timesteps, **cond, return_dict=False)[0]
+        pred_a = self.unet(xt_a, timesteps, **cond, return_dict=False)[0]
+        # EraseDiff's forget target: uniform noise drawn after the second forward (ddpm_deletion_loss.py:75)
+        if self.loss_fn == "erasediff" and forget_target is None and rng is not None:
+            # opt-in device RNG: the uniform target is drawn inside the kernel (aux domain of this micro-step's draw)
+            if draw is None:
+                draw = rng.next_draw()
+            per_row = x0.numel() // max(x0.shape[0], 1)
+            g_x, g_a, rl_x, rl_a, _ = ops.dual_mse_rng_fwd_bwd(
+                pred_x.detach(), pred_a.detach(), noise, self.go, self.go, rng.seed, draw,
+                elem_offset=rng.row_offset * per_row, d_draw=rng.d_draw)
+        else:
+            if self.loss_fn == "erasediff":
+                tgt_a = torch.rand_like(pred_a) if forget_target is None else forget_target
+            else:
+                tgt_a = noise
+            tgt_x = noise
+            if tgt_a.dtype != tgt_x.dtype:
+                tgt_x = tgt_x.to(tgt_a.dtype)
+            g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a, self.go, self.go)
+        cb.begin_x()
+        torch.autograd.backward(pred_x, g_x)
+        cb.begin_a(last_micro_step=last)
+        torch.autograd.backward(pred_a, g_a)
+        out.update(row_loss_x=rl_x, row_loss_a=rl_a)
+        return draw
+
+    def _micro_single_term(self, x0, a0, noise, timesteps, cond, out) -> None:
+        """naive_del / simple_neg_del: one forward, one backward, no combine (delete_celeb.py:682-684)."""
+        if self.loss_fn == "naive_del":
+            xt = self.scheduler.add_noise(x0, noise, timesteps)
+            alpha = 1.0
+        else:
+            xt = self.scheduler.add_noise(a0, noise, timesteps)
+            alpha = -float(self.superfactor)
+        pred = self.unet(xt, timesteps, **cond, return_dict=False)[0]
+        # grad = (go * alpha) * 2 (pred - eps): dual kernel with the second term switched off
+        g, _unused, rl, _ = ops.dual_mse_fwd_bwd(pred.detach(), pred.detach(), noise, noise,
+                                                 float(np.float32(self.go) * np.float32(alpha)), 0.0)
+        self.combiner.begin_x()
+        torch.autograd.backward(pred, g)
+        out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl
 
     def end_of_optimizer_step(self) -> None:
         """Bookkeeping at the accumulation boundary: restart the micro-step count and, for
