@@ -70,14 +70,16 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        # Not a fallback: the only thing tried is compiling the SAME CUDA library in place (needs nvcc).
+    # Not a fallback: the only thing tried is compiling the SAME CUDA library in place (needs nvcc). build() returns
+    # at once when the library matches the content hash of its sources, so a kernel edit can never run a stale .so.
+    from . import build as _build
+    if _build.needs_build():
         try:
-            from . import build as _build
             _build.build()
         except Exception as e:
+            what = "is stale (its sources changed since it was built)" if LIB_PATH.exists() else "not found"
             raise SissLibraryError(
-                f"{LIB_PATH} not found and could not be built ({e}). Build it with `python -m siss_b200.build` "
+                f"{LIB_PATH} {what} and could not be built ({e}). Build it with `python -m siss_b200.build` "
                 "(or __graft_entry__.build()). siss_b200 has no CPU or PyTorch fallback.") from e
     try:
         lib = ctypes.CDLL(str(LIB_PATH))
@@ -106,14 +108,14 @@ def check(code: int, what: str) -> None:
         raise SissLibraryError(f"{what} failed with code {code}: {error_string(code)}")
 
 
-_device_checked = False
+_devices_checked = set()
 
 
-def require_b200() -> None:
-    """Raise unless the current CUDA device is sm_100. Called once by the first op."""
-    global _device_checked
-    if _device_checked:
+def require_b200(device_index: int = -1) -> None:
+    """Raise unless the CUDA device the op runs on is sm_100. Checked once per device (the library keeps its
+    per-device launch state — shared-memory opt-ins, SM counts — keyed by device as well)."""
+    if device_index in _devices_checked:
         return
     sm, major, minor = c_int(), c_int(), c_int()
     check(load().siss_check_device(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "siss_check_device")
-    _device_checked = True
+    _devices_checked.add(device_index)

@@ -14,6 +14,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libsiss_b200.so"
+HASH_PATH = PKG_DIR / "libsiss_b200.so.srchash"
 SOURCES = ["rowwise.cu", "wmse.cu", "combine.cu", "p2p.cu", "stats.cu", "optim.cu", "multitensor.cu", "membership.cu", "rng.cu"]
 
 NVCC_FLAGS = [
@@ -31,13 +32,28 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found: libsiss_b200.so cannot be built (set NVCC=/path/to/nvcc)")
 
 
-def needs_build() -> bool:
-    if not LIB_PATH.exists():
-        return True
-    built = LIB_PATH.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES if (CSRC / s).exists()] + list(CSRC.glob("*.cuh"))
+def source_hash() -> str:
+    """SHA-256 over everything the library is compiled from (sources, headers, flags). Stored next to the built
+    library (``libsiss_b200.so.srchash``) so that a stale ``.so`` is detected by CONTENT — file times do not survive
+    the snapshot copy to a GPU box, and an edit that leaves the ABI version unchanged must still trigger a rebuild."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted([CSRC / s for s in SOURCES if (CSRC / s).exists()] + list(CSRC.glob("*.cuh")))
     deps.append(PKG_DIR.parent / "include" / "siss_b200.h")
-    return any(d.stat().st_mtime > built for d in deps)
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
+        return True
+    try:
+        return HASH_PATH.read_text().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -63,6 +79,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         sys.stderr.write(proc.stderr)
     os.replace(tmp, LIB_PATH)
+    htmp = HASH_PATH.with_name(f"{HASH_PATH.name}.tmp.{os.getpid()}")
+    htmp.write_text(source_hash() + "\n")
+    os.replace(htmp, HASH_PATH)
     return LIB_PATH
 
 

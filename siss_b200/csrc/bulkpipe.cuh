@@ -316,12 +316,13 @@ pipe_row_kernel(typename Op::Params p, RowWorkspace ws, RowSched s) {
 
 template <class Op>
 static int launch_pipe(const typename Op::Params& p, RowWorkspace ws, long long B, long long D, int W, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[kMaxDevices] = {false};   // the opt-in is a per-device function attribute
     constexpr int smem = PipeSmem<Op>::bytes();
-    if (!configured) {
+    const int slot = current_device_slot();
+    if (!configured[slot] || slot == kMaxDevices - 1) {
         cudaError_t e = cudaFuncSetAttribute(pipe_row_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[slot] = true;
     }
     RowSched s = make_row_sched(B, D, W, Op::kOcc);
     // Oversubscription: `over` spans per resident CTA slot, span id == blockIdx.x, so the HARDWARE CTA scheduler

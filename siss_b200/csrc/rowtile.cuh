@@ -42,6 +42,8 @@ struct RowSched {
                      // vs 31.6 us static); kept out, see DESIGN.md.
 };
 
+constexpr int kMaxDevices = 64;           // per-device launch state tables (one process may drive several GPUs)
+int current_device_slot();
 int cached_sm_count();
 
 // tuning knobs for the dynamically scheduled kernels (read once; see tools/ for the sweep that set the defaults)

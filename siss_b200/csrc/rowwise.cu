@@ -14,15 +14,25 @@
 
 namespace siss {
 
+// Current CUDA device, clamped to the size of the per-device state tables (function attributes and SM counts belong
+// to a device/context, not to the process: one process may drive several GPUs).
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 int cached_sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
+    static int sms[kMaxDevices] = {0};
+    const int slot = current_device_slot();
+    if (sms[slot] == 0) {
+        int v = 0, dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = kNumSMsB200;
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = kNumSMsB200;
+        sms[slot] = v;
     }
-    return sms;
+    return sms[slot];
 }
 
 int env_int(const char* name, int dflt) {

@@ -34,8 +34,12 @@ class DeviceFeeder:
 
     def submit(self, host_tensors: Sequence[torch.Tensor]) -> None:
         """Enqueue the H2D copy of one batch (pinned host tensors) on the copy stream."""
-        if self._submitted - self._consumed >= self.depth:
-            raise RuntimeError("DeviceFeeder: all slots are in flight; call next() first")
+        # occupied slots = copies submitted but not yet handed out + the slot the last next() handed out, which the
+        # compute stream is still reading until the following next() records its `_free` event
+        occupied = (self._submitted - self._consumed) + (1 if self._in_use >= 0 else 0)
+        if occupied >= self.depth:
+            raise RuntimeError("DeviceFeeder: all slots are in flight (the batch returned by the last next() still "
+                               "counts as in use); call next() first")
         k = self._submitted % self.depth
         for t in host_tensors:
             if not t.is_pinned():

@@ -75,14 +75,24 @@ class GradCombiner:
             raise ValueError(f"unknown transport {transport!r}")
         want_p2p = transport == "p2p" or (transport == "auto" and self.world in (2, 4))
         if self.world > 1 and want_p2p and dev.type == "cuda":
+            err = None
             try:
                 from .p2p import PeerExchange
                 self.peer = PeerExchange(self.total, dev, process_group)
             except Exception as e:
                 if transport == "p2p":
                     raise
-                import warnings
-                warnings.warn(f"siss_b200: peer-memory transport unavailable ({e!r}); using NCCL collectives")
+                err = e
+                self.peer = None
+            # The choice must be COLLECTIVE: a rank that fell back on its own would issue NCCL collectives while its
+            # peers launch peer-memory kernels and wait in symmetric-memory barriers — a deadlock at the first combine().
+            ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0:
+                if self.peer is not None or err is not None:
+                    import warnings
+                    warnings.warn("siss_b200: peer-memory transport unavailable on at least one rank "
+                                  f"({err!r}); every rank uses NCCL collectives")
                 self.peer = None
         if self.peer is not None:
             self.g_x, self.g_a = self.peer.g_x, self.peer.g_a

@@ -53,7 +53,11 @@ def _need_cuda(*tensors: torch.Tensor) -> torch.device:
             dev = t.device
         elif t.device != dev:
             raise SissLibraryError(f"tensors on different devices: {dev} vs {t.device}")
-    _lib.require_b200()
+    if dev is not None:
+        if dev.index != torch.cuda.current_device():
+            raise SissLibraryError(f"tensors live on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                                   "kernels launch on the current device's stream (use torch.cuda.device(...))")
+        _lib.require_b200(dev.index)
     return dev
 
 

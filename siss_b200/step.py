@@ -175,8 +175,18 @@ class UnlearnStep:
                 tgt_a = noise
             tgt_x = noise
             if tgt_a.dtype != tgt_x.dtype:
-                tgt_x = tgt_x.to(tgt_a.dtype)
-            g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a, self.go, self.go)
+                # eager promotes (pred - noise) and (pred - uniform) independently (ddpm_deletion_loss.py:62,72-76); the
+                # kernel takes one target dtype, so both go to the WIDER one — never round fp32 noise down to 16 bits
+                wide = torch.promote_types(tgt_x.dtype, tgt_a.dtype)
+                tgt_x, tgt_a = tgt_x.to(wide), tgt_a.to(wide)
+            px, pa = pred_x.detach(), pred_a.detach()
+            if px.dtype != torch.float32 and tgt_x.dtype == torch.float32:
+                # 16-bit UNet output against an fp32 target: eager computes the loss in fp32 and autograd rounds the
+                # gradient back to the prediction dtype — same here (rare: accelerate's autocast returns fp32)
+                g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(px.float(), pa.float(), tgt_x, tgt_a, self.go, self.go)
+                g_x, g_a = g_x.to(px.dtype), g_a.to(pa.dtype)
+            else:
+                g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(px, pa, tgt_x, tgt_a, self.go, self.go)
         cb.begin_x()
         torch.autograd.backward(pred_x, g_x)
         cb.begin_a(last_micro_step=last)

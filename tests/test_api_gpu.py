@@ -520,3 +520,26 @@ def test_device_feeder_orders_and_protects_slots(dev):
         feeder.next()                                   # nothing submitted
     with pytest.raises(ValueError):
         feeder.submit([torch.zeros(shape).bfloat16(), torch.zeros(shape).bfloat16()])   # not pinned
+
+
+def test_device_feeder_counts_the_handed_out_slot_as_occupied(dev):
+    """submit, submit, next, submit (depth 2): the third submit would reuse slot 0, which the consumer of the batch
+    just handed out is still reading — it must be refused, and the data of batch 0 must stay intact."""
+    from siss_b200.feed import DeviceFeeder
+    shape = (4, 3, 32, 32)
+    feeder = DeviceFeeder([shape], [torch.float32], dev, depth=2)
+    hosts = [[torch.full(shape, float(i)).pin_memory()] for i in range(3)]
+    feeder.submit(hosts[0])
+    feeder.submit(hosts[1])
+    with pytest.raises(RuntimeError):
+        feeder.submit(hosts[2])                         # both slots pending
+    (x0,) = feeder.next()
+    with pytest.raises(RuntimeError):
+        feeder.submit(hosts[2])                         # slot 0 handed out and in use, slot 1 pending
+    torch.cuda.synchronize()
+    assert float(x0.mean()) == 0.0
+    (x1,) = feeder.next()                               # releases slot 0
+    feeder.submit(hosts[2])                             # now allowed: lands in slot 0
+    (x2,) = feeder.next()
+    torch.cuda.synchronize()
+    assert float(x1.mean()) == 1.0 and float(x2.mean()) == 2.0
