@@ -75,6 +75,18 @@ inline RowSched make_row_sched(long long B, long long D, int W, int ctas_per_sm,
     return s;
 }
 
+// Oversubscribed launch of the register-staged (LDG) kernels: `k` spans per resident CTA slot, span id == blockIdx.x,
+// so the hardware CTA scheduler balances SM-to-SM speed differences (experiment knob SISS_LDG_OVERSUB; spans never
+// shorter than `vpt` units per thread).
+inline void oversubscribe(RowSched& s, int k, int vpt) {
+    if (k <= 1) return;
+    long long g = (long long)s.grid * k;
+    const long long by_size = s.U / ((long long)kThreads * vpt);
+    if (g > by_size) g = by_size;
+    if (g > kMaxSpans) g = kMaxSpans;
+    if (g > s.grid) { s.grid = (int)g; s.nspans = (int)g; }
+}
+
 // span c: [floor(c U / S), floor((c+1) U / S)),  S = nspans
 __device__ __forceinline__ void span_range(const RowSched& s, long long c, long long& u0, long long& u1) {
     const long long g = s.nspans;

@@ -362,6 +362,8 @@ static int launch_mixture(const void* src_x, const void* src_a, const void* x0, 
     }
     if (vec) {
         RowSched s = make_row_sched(B, D, N, kK2Occ);
+        static const int over = env_int("SISS_LDG_OVERSUB", 1);
+        oversubscribe(s, over, kK2Vpt);
         mixture_kernel<T, N, FUSED, RNG><<<s.grid, kThreads, 0, st>>>(
             (const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
             gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a, rng, d_draw, elem_offset, (T*)noise_out, ws, s);

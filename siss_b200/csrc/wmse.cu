@@ -630,6 +630,8 @@ static int launch_wmse_fwd_bwd(const void* pred, const void* x_mix, const void* 
     }
     if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a)) {
         RowSched rt = make_row_sched(B, D, W, kK3Occ);
+        static const int over = env_int("SISS_LDG_OVERSUB", 1);
+        oversubscribe(rt, over, kK3Vpt);
         wmse_fwd_bwd_kernel<TP, T, W, true><<<rt.grid, kThreads, 0, st>>>(
             (const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps, w_x, w_a,
             go_x, go_a, (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a, ws, rt);

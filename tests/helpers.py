@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
-GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz") if not p.stem.startswith(("membership_", "step_")))
+GOLDEN_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz") if not p.stem.startswith(("membership_", "step_", "fullshape_")))
+FULLSHAPE_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("fullshape_*.npz"))     # make_golden_fullshape.py
 STEP_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("step_*.npz"))               # make_golden_step.py
 MEMBERSHIP_CASES = sorted(p.stem for p in GOLDEN_DIR.glob("membership_*.npz"))   # make_golden_membership.py
 
@@ -59,9 +60,15 @@ def conditioning_of(case: Dict[str, object]) -> Dict[str, torch.Tensor]:
     return {}
 
 
-def weight_tolerance(d_x: torch.Tensor, d_a: torch.Tensor, k: float = 8.0) -> torch.Tensor:
+def weight_tolerance(d_x: torch.Tensor, d_a: torch.Tensor, k: float = 1.8) -> torch.Tensor:
     """Relative tolerance on an importance weight whose exponent difference carries fp32 summation
-    noise: |delta(d_x - d_a)| <= k * eps32 * (d_x + d_a); d(log w) <= |delta|. Plus 1e-5 floor."""
+    noise: |delta(d_x - d_a)| <= k * eps32 * (d_x + d_a); d(log w) <= |delta|. Plus 1e-5 floor.
+
+    k is MEASURED, not guessed: the reference's own fp32 weights deviate from the float64 evaluation by up to 0.93 of
+    these units at B = 64 x 3x256x256 (fp32 and bf16 latents, t = 999 and uniform t; torch CPU — the fixtures' origin —
+    and eager CUDA, tests/test_fullshape_golden.py) and by <= 0.28 on the small fixtures; the kernel itself is 1e-5-close
+    to float64, so kernel-vs-reference is bounded by the reference's error. k = 1.8 is < 2x that measurement (round 1
+    used 8, a 19 % window at the celeb shape; this is ~4 %)."""
     eps = torch.finfo(torch.float32).eps
     return k * eps * (d_x.abs() + d_a.abs()).double() + 1e-5
 
