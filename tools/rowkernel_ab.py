@@ -64,8 +64,13 @@ def main():
     c12s, c12d = torch.zeros(bytes12 // 2, dtype=torch.uint8, device=dev), torch.empty(bytes12 // 2, dtype=torch.uint8, device=dev)
     c3s, c3d = torch.zeros(bytes3 // 2, dtype=torch.uint8, device=dev), torch.empty(bytes3 // 2, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # A filler that keeps the stream busy (~170 us) while the host enqueues the two bracketed launches: a bracket on an
+    # IDLE stream would time the host's ctypes call, not the kernel (first version of this tool: 38 / 77 us instead of
+    # 29 / 48). It also flushes L2, like the 2.3 GB of K4 traffic between two steps of bench.py.
+    filler = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
     for i in range(args.iters + 5):
         x0, a0, nz, pred = sets[i % nsets]
+        filler.zero_()
         out = bracket("k12", lambda: ops.add_noise_mixture(x0, a0, nz, keep, t, ac, gamma, sigma, 0.5))
         x_mix, _, _, w_x, w_a = out
         bracket("k3", lambda: ops.wmse_fwd_bwd(pred, x_mix, x0, a0, t, gamma, sigma, w_x, w_a, go, go))
