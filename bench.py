@@ -314,10 +314,10 @@ def workload_config(args, n):
         "per_gpu_batch": args.batch, "global_batch": args.batch * n, "shape": [args.channels, args.res, args.res],
         "latent_dtype": args.dtype, "pred_dtype": "fp32", "timesteps": "t=999 (delete_celeb.py:593)",
         "grad_params": args.params, "grad_accum": 1, "unet": "outside the path (resident eps_hat / P-param stub in e2e)",
-        "parallelism": f"dp{n}", "transport": getattr(args, "_transport", "single" if n == 1 else "nccl"), "l2": "inputs larger than L2 (per-step footprint >> 126 MB); no flush",
-        "resident_step": ("K1oK2 + K3 + K4a + K4b; N>1: + gradient exchange — transport p2p = fused NVLink peer-memory "
-                          "kernels (reduce-scatter x2 + K4a | K4b + all-gather), transport nccl = reduce-scatter x2, "
-                          "3-scalar all-reduce, all-gather around K4a/K4b"),
+        "parallelism": f"dp{n}", "l2": "inputs larger than L2 (per-step footprint >> 126 MB); no flush",
+        "resident_step": ("K1oK2 + K3 + K4a + K4b; N>1: + the data-parallel gradient sum around K4 (fused peer-memory / "
+                          "NVSwitch-multicast kernels or NCCL collectives: the schedule used is reported in comm.schedule, "
+                          "not here, so that both arms print one config)"),
     }
 
 
@@ -564,33 +564,27 @@ def run_siss(args):
     keep = (torch.rand(B, generator=torch.Generator().manual_seed(7)) > lambd).to(torch.uint8).to(dev)
     pad = 4 * n
     Ptot = (P + pad - 1) // pad * pad
-    peer = None
-    transport = "single" if n == 1 else "nccl"
-    if n > 1 and (args.transport == "p2p" or (args.transport == "auto" and n in (2, 4))):
-        try:
-            from siss_b200.p2p import PeerExchange
-            peer = PeerExchange(Ptot, dev)
-            transport = "p2p"
-        except Exception as e:  # symmetric memory not available: NCCL collectives
-            if args.transport == "p2p":
-                raise
-            print(f"[bench] peer-memory transport unavailable: {e!r}", file=sys.stderr)
-    if peer is not None:
-        G_x, G_a = peer.g_x, peer.g_a
+    comb = None
+    transport = "single"
+    if n > 1:
+        # the exchange goes through the public GradCombiner: fused peer-memory / NVSwitch-multicast kernels or NCCL
+        # collectives, chosen by --transport or (auto) by a start-up measurement on these very buffers
+        holder = torch.nn.Parameter(torch.empty(P, device=dev))
+        comb = GradCombiner([holder], transport=args.transport)
+        assert comb.total == Ptot
+        transport = comb.transport
+        G_x, G_a = comb.g_x, comb.g_a
         G_x.copy_(torch.randn(Ptot, generator=gen, device=dev) * 1e-3)
         G_a.copy_(torch.randn(Ptot, generator=gen, device=dev) * 1e-3)
     else:
         G_x = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
         G_a = torch.randn(Ptot, generator=gen, device=dev) * 1e-3
-    G_out = torch.empty_like(G_x)
+    G_out = torch.empty_like(G_x) if n == 1 else None
     sums = torch.zeros(3, dtype=torch.float64, device=dev)
     stats5 = torch.zeros(5, device=dev)
-    if n > 1:
-        S = Ptot // n
-        sh_x, sh_a = torch.empty(S, device=dev), torch.empty(S, device=dev)
 
-    if peer is not None:
-        kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_p2p_exchange_combine"]
+    if n > 1:
+        kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_exchange_combine"]
     else:
         kernels = ["siss_add_noise_mixture", "siss_wmse_fwd_bwd", "siss_norm3", "siss_combine"]
     evs = {k: [] for k in kernels}
@@ -613,20 +607,12 @@ def run_siss(args):
             timed("siss_norm3", record, lambda: ops.norm3(G_x, G_a, out=sums))
             timed("siss_combine", record, lambda: ops.combine(G_x, G_a, sums, _lib.SISS_COMBINE_SCALING_NORM,
                                                               scaling_norm, max_norm, out=G_out, stats=stats5))
-        elif peer is not None:
-            # fused: barrier | reduce-scatter x2 + K4a over peer loads | barrier | K4b + all-gather over peer stores | barrier
-            timed("siss_p2p_exchange_combine", record, lambda: peer.combine(_lib.SISS_COMBINE_SCALING_NORM, scaling_norm,
-                                                                           max_norm, False, stats5))
         else:
-            dist.reduce_scatter_tensor(sh_x, G_x)
-            dist.reduce_scatter_tensor(sh_a, G_a)
-            timed("siss_norm3", record, lambda: ops.norm3(sh_x, sh_a, out=sums))
-            dist.all_reduce(sums)
-            timed("siss_combine", record, lambda: ops.combine(sh_x, sh_a, sums, _lib.SISS_COMBINE_SCALING_NORM,
-                                                              scaling_norm, max_norm, out=sh_x, stats=stats5))
-            dist.all_gather_into_tensor(G_out, sh_x)
+            # sum over ranks + K4a + K4b, result in every rank's G_x (in place): 2-3 fused kernels with stream-ordered
+            # symmetric-memory barriers between them, or NCCL collectives around K4a / K4b
+            timed("siss_exchange_combine", record, lambda: comb.exchange(_lib.SISS_COMBINE_SCALING_NORM, scaling_norm,
+                                                                       max_norm, False))
 
-    args._transport = transport
     for _ in range(max(args.warmup, 3)):
         resident_step()
     barrier()
@@ -643,22 +629,34 @@ def run_siss(args):
         gpu_launches = ops.launch_count - launches0
         # timed region 2: the same K steps again with a CUDA-event bracket around every kernel launch ->
         # per-kernel durations for the roofline (each bracket costs the stream a few microseconds, which is
-        # why it is kept out of region 1; bracketed durations are therefore slightly pessimistic)
-        empty_brackets = []
-        for _ in range(args.steps):
-            resident_step(record=True)
-            s_e, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s_e.record(); e_e.record()                      # an EMPTY bracket on the same busy stream (calibration)
-            empty_brackets.append((s_e, e_e))
-        barrier()
-    empty_bracket_us = 1e3 * statistics.mean(a.elapsed_time(b) for a, b in empty_brackets)
-    elapsed_ms = start.elapsed_time(end)
+        # why it is kept out of region 1). Reported per kernel: the MEDIAN bracket after dropping the first two.
+        def bracket_pass():
+            for k in kernels:
+                evs[k].clear()
+            empties = []
+            for _ in range(args.steps):
+                resident_step(record=True)
+                s_e, e_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_e.record(); e_e.record()                  # an EMPTY bracket on the same busy stream (calibration)
+                empties.append((s_e, e_e))
+            barrier()
+            ms = {k: statistics.median([a.elapsed_time(b) for a, b in v][2:] or [a.elapsed_time(b) for a, b in v])
+                  for k, v in evs.items()}
+            return ms, 1e3 * statistics.median(a.elapsed_time(b) for a, b in empties)
+
+        elapsed_ms = start.elapsed_time(end)
+        kernel_ms, empty_bracket_us = bracket_pass()
+        bracket_passes = 1
+        # the brackets must add up to the un-instrumented step (plus a few us of bracket cost); if they do not, the
+        # pass was disturbed (clock ramp, another tenant on the host) — measure it again rather than report it
+        while n == 1 and sum(kernel_ms.values()) > 1.05 * (elapsed_ms / args.steps) and bracket_passes < 3:
+            kernel_ms, empty_bracket_us = bracket_pass()
+            bracket_passes += 1
     el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed_ms = float(el.item())
     value = B * n * args.steps / (elapsed_ms / 1e3)
-    kernel_ms = {k: statistics.mean(s.elapsed_time(e) for s, e in v) for k, v in evs.items()}
 
     # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md): s_in = bytes of the latent dtype
     s_in = x0.element_size()
@@ -668,12 +666,69 @@ def run_siss(args):
         "siss_wmse_fwd_bwd": (12 + 3 * s_in) * B * D,
         "siss_norm3": 8 * Pk,
         "siss_combine": 12 * Pk,
-        # NVLink bytes per rank: (N-1)/N * (8 in + 4 out) B/param; reported against HBM peak only for reference
-        "siss_p2p_exchange_combine": 12 * (Ptot - Pk),
     }
+    wire = comb.wire_bytes() if n > 1 else None
+    if n > 1:
+        # the exchange is NVLink-bound: its "bytes" are what crosses this GPU's ports in the busier direction
+        alg_bytes["siss_exchange_combine"] = max(wire["out_bytes"], wire["in_bytes"])
     peak, peak_src = load_peaks()
     per_kernel = {k: {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "gbs": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9,
-                      "frac": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak} for k in kernels}
+                      "frac": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak} for k in kernels
+                  if k != "siss_exchange_combine"}
+    comm = None
+    if n > 1:
+        # NVLink reference: peer copy 770 GB/s per direction per GPU (B200_PROFILING.md, measured on this pool; 900 nominal)
+        link = 770.0
+        ex_ms = kernel_ms["siss_exchange_combine"]
+        busier = max(wire["out_bytes"], wire["in_bytes"])
+        local_ms = sum(v for k, v in kernel_ms.items() if k != "siss_exchange_combine")
+        p2p_bytes = 12 * (Ptot - Pk)            # the three-stage peer-memory / ring count, for comparison
+        comm = {"schedule": wire["schedule"], "wire_bytes_out": wire["out_bytes"], "wire_bytes_in": wire["in_bytes"],
+                "wire_bytes_three_stage_p2p": p2p_bytes, "exchange_ms": ex_ms,
+                "achieved_gbs_busier_direction": busier / (ex_ms * 1e-3) / 1e9,
+                "link_ceiling_gbs": link, "link_ceiling_source": "B200_PROFILING.md: measured peer copy per direction per GPU",
+                "frac_of_link_ceiling": busier / (ex_ms * 1e-3) / 1e9 / link,
+                "min_exchange_ms_at_ceiling": busier / link / 1e6,
+                "min_step_ms_at_ceiling": local_ms + busier / link / 1e6,
+                "tuning_ms": dict(comb.tuning), "transport_arg": args.transport,
+                "note": ("bytes cross this GPU's NVLink ports per exchange in each direction for the schedule in use; the step "
+                         "at N > 1 is the exchange (K1-K3 take ~0.08 ms), so hot-path-only weak scaling is bounded by "
+                         "min_step_ms_at_ceiling, not by the kernels")}
+        # ---- self-check of the exchange (not timed): fresh per-rank gradients -> exchange -> compare with a 1-rank
+        # evaluation (rank-ordered sum of every rank's buffers, siss_norm3, siss_combine) recomputed on every rank
+        try:
+            gchk = torch.Generator(device=dev).manual_seed(555 + rank)
+            G_x.copy_(torch.randn(Ptot, generator=gchk, device=dev) * 1e-3)
+            G_a.copy_(torch.randn(Ptot, generator=gchk, device=dev) * 1e-3)
+            allx, alla = torch.empty(n, Ptot, device=dev), torch.empty(n, Ptot, device=dev)
+            dist.all_gather_into_tensor(allx.view(-1), G_x)
+            dist.all_gather_into_tensor(alla.view(-1), G_a)
+            X, A = allx[0].clone(), alla[0].clone()
+            for r in range(1, n):
+                X += allx[r]; A += alla[r]
+            del allx, alla
+            ref_sums = ops.norm3(X, A)
+            ref_out, ref_stats = ops.combine(X, A, ref_sums, _lib.SISS_COMBINE_SCALING_NORM, scaling_norm, max_norm)
+            got_stats = comb.exchange(_lib.SISS_COMBINE_SCALING_NORM, scaling_norm, max_norm, False).clone()
+            torch.cuda.synchronize()
+            err = float((G_x - ref_out).abs().max()) / float(ref_out.abs().max())
+            srel = float(((got_stats - ref_stats).abs() / ref_stats.abs().clamp_min(1e-30)).max())
+            sig = torch.cat([got_stats.view(torch.int32).to(torch.int64), G_x.view(torch.int32).sum(dtype=torch.int64).reshape(1)])
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(lo, hi))
+            ok = same and err <= 2e-6 and srel <= 2e-6
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            exchange_check = "ok" if int(flag.item()) == 1 else (f"FAILED: ranks identical={same}, max|out-ref|/max|ref|={err:.2e}, "
+                                                                f"stats rel err={srel:.2e}")
+            comm["exchange_check_detail"] = {"max_abs_err_over_peak": err, "stats_rel_err": srel, "ranks_bit_identical": same,
+                                             "stats5": got_stats.tolist(), "stats5_one_rank": ref_stats.tolist()}
+            del X, A, ref_out
+        except Exception as e:  # never lose the bench line to the checker
+            exchange_check = f"ERROR: {e!r}"
+    else:
+        exchange_check = None
     if n == 1 and not args.no_copy_floor:
         # Size floor: a plain device-to-device copy that moves the SAME number of bytes as each kernel (half read, half
         # written), under the same event bracket, L2 flushed before every copy. MEASURED_PEAKS is a large-buffer
@@ -695,16 +750,26 @@ def run_siss(args):
             per_kernel[k]["vs_copy_same_bytes"] = per_kernel[k]["copy_same_bytes_ms"] / kernel_ms[k]
             del src, dst
         del flush
-    dom = max(kernels, key=lambda k: kernel_ms[k])
+    # The reported kernel is chosen by ALGORITHMIC BYTES among the HBM-bound kernels of the step (K4b at N = 1; at N > 1
+    # K4 runs inside the NVLink-bound exchange, which has its own `comm` block, so K3 is the largest HBM-bound launch):
+    # a choice that does not depend on the noise of one timing.
+    hbm_kernels = [k for k in kernels if k != "siss_exchange_combine"]
+    dom = max(hbm_kernels, key=lambda k: alg_bytes[k])
+    share = sum(kernel_ms.values()) / (elapsed_ms / args.steps)
+    frac_ok = share <= 1.05 or n > 1
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": per_kernel[dom]["frac"], "traffic": load_traffic(dom), "peak_source": peak_src,
+                "frac": per_kernel[dom]["frac"] if frac_ok else None, "traffic": load_traffic(dom), "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes[dom], "ms_per_launch": kernel_ms[dom], "kernels": per_kernel,
+                "timing": "median CUDA-event bracket per launch (first two dropped), second timed region",
+                "bracket_passes": bracket_passes,
+                "rejected": None if frac_ok else (f"kernel brackets sum to {share:.3f} of the un-instrumented step after "
+                                                  f"{bracket_passes} passes: per-kernel timings disturbed, no frac reported"),
                 "empty_event_bracket_us": empty_bracket_us,
                 "bracket_note": ("per-kernel ms are CUDA-event brackets around single launches in a second timed region; an empty "
                                  "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/; "
                                  "copy_same_bytes_ms = a plain D2D copy moving the kernel's algorithmic bytes under the same "
                                  "bracket with L2 flushed (the floor at that size), vs_copy_same_bytes = that / kernel ms"),
-                "kernel_share_of_step": sum(kernel_ms.values()) / (elapsed_ms / args.steps),
+                "kernel_share_of_step": share,
                 "l2_note": ("siss_combine re-reads what siss_norm3 just streamed; siss_norm3 leaves the last SISS_L2_KEEP_MB "
                             "(default 80) MB of the buffers in L2 with an evict_last policy and the combine walks in reverse, so "
                             "~6 % of its algorithmic bytes never reach DRAM and frac may exceed 1. `traffic` is an ncu capture, "
@@ -717,7 +782,8 @@ def run_siss(args):
         torch.cuda.empty_cache()
         unet = BenchUNet(P).to(dev)
         del G_x, G_a
-        peer = None
+        comb = None
+        holder = None
         torch.cuda.empty_cache()
         comb = GradCombiner(unet.parameters(), transport=args.transport)
         step = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B * n,
@@ -837,7 +903,8 @@ def run_siss(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roofline, "comm": comm, "exchange_check": exchange_check,
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(), "unlearn_steps": unlearn, "other_configs": others,
             "eager_gpu_reference": eager_ref,
         }

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SISS_B200_ABI_VERSION 2
+#define SISS_B200_ABI_VERSION 3
 
 enum siss_dtype { SISS_F32 = 0, SISS_BF16 = 1, SISS_F16 = 2 };
 
@@ -338,9 +338,10 @@ int siss_batch_stats(const float* row_loss_x, const float* row_loss_a, const flo
  * order, writes the reduced shard to shard_x / shard_a (local), writes this rank's three partial sums
  * to sums3_local and to doubles [4*rank .. 4*rank+2] of every peer's scalar buffer h_peer_scalars[r]
  * (each at least 4*world doubles). Inbound NVLink bytes per rank: (world-1)/world * 8 per parameter.
- * x_prereduced != 0: shard_x already holds the reduced G_x shard (its reduce-scatter was overlapped with
+ * x_prereduced == 1: shard_x already holds the reduced G_x shard (its reduce-scatter was overlapped with
  * the second backward pass, G_x being final after the first); only G_a crosses NVLink (4 B/parameter)
- * and h_peers_x is ignored.
+ * and h_peers_x is ignored. x_prereduced == 2: G_a ONLY (first phase of the pipelined exchange below):
+ * h_peers_x / shard_x are ignored, the published sums are {0, sum a^2, 0}.
  *
  * siss_p2p_combine_allgather: K4b + all-gather in one kernel. Sums the `world` scalar slots (local
  * copy, rank order, so every rank derives identical s and clip), computes
@@ -371,6 +372,53 @@ int siss_p2p_adamw_allgather(const float* shard_x, const float* shard_a, const d
                              float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
                              double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
                              float* ema_shard, double ema_decay, float* stats5, siss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The same exchange through the NVSwitch's in-fabric reduction / replication (NVLS). `mc_*` are MULTICAST device
+ * addresses bound to the same symmetric allocation on every rank (cuMulticast*, e.g. torch symmetric memory's
+ * `multicast_ptr`): `multimem.ld_reduce` returns the sum over all ranks of the addressed 16 bytes (inbound bytes /
+ * world), `multimem.st` replicates a store into every rank's buffer (outbound bytes / world). The fp32 additions
+ * happen in the switch in a fabric-defined order: every rank still holds bit-identical results (each element is
+ * reduced once, by its owner), but they are not bit-equal to the rank-ordered sums of the siss_p2p_* kernels.
+ * Barriers exactly as for the siss_p2p_* pair. Replaces the same reference sites (delete_celeb.py:691, 714-767).
+ *
+ * siss_nvls_reduce_norm3      reduce-scatter + K4a. x_mode 0: G_x and G_a through the switch; 1: shard_x already
+ *                             reduced, G_a through the switch; 2: G_a only (published sums {0, sum a^2, 0}).
+ * siss_nvls_combine_allgather K4b on the shard + one multimem.st per vector (all-gather in the switch) into mc_out.
+ * siss_nvls_adamw_allgather   ZeRO-1 step as siss_p2p_adamw_allgather, new parameters replicated through mc_param;
+ *                             param_local = THIS rank's (unicast) flat parameter buffer.
+ *
+ * PIPELINED exchange for the scaling-norm modes (SISS / SISS No-IS, s = scaling_norm / ||G_a||, delete_celeb.py:746):
+ * the reduce of G_x (outbound-heavy) and the gather of the result (inbound-heavy) run concurrently in one kernel.
+ *   1. siss_p2p_reduce_norm3(x_prereduced = 2) or siss_nvls_reduce_norm3(x_mode = 2)      | barrier
+ *   2. siss_nvls_xcombine_bcast: for the own shard x = multimem.ld_reduce(G_x), y = x - s * shard_a (s from the
+ *      phase-1 slots `scalar_slots1`), multimem.st(y) IN PLACE into every rank's G_x; publishes
+ *      {sum x^2, sum x a, sum y^2} to doubles [4*rank ..] of every peer's second slot array h_peer_scalars2[r] | barrier
+ *   3. siss_scale_finalize (local): n_x, n_a, s, total_norm = sqrt(sum y^2), clip (clip_grad_norm_, :767) -> stats5,
+ *      and g *= clip over the whole local buffer (skipped when clip == 1).
+ * ---------------------------------------------------------------------------------------- */
+int siss_nvls_reduce_norm3(const float* mc_x, const float* mc_a, double* const* h_peer_scalars,
+                           int world, int rank, int64_t shard_len, float* shard_x, float* shard_a,
+                           double* sums3_local, int x_mode, void* workspace, siss_stream_t stream);
+
+int siss_nvls_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                                float* mc_out, int world, int rank, int64_t shard_len,
+                                int mode, float value, float max_norm, int inf_guard, float* stats5,
+                                siss_stream_t stream);
+
+int siss_nvls_adamw_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                              float* mc_param, const float* param_local, int world, int rank, int64_t shard_len,
+                              int mode, float value, float max_norm, int inf_guard,
+                              float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                              double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
+                              float* ema_shard, double ema_decay, float* stats5, siss_stream_t stream);
+
+int siss_nvls_xcombine_bcast(float* mc_x, const float* shard_a, const double* scalar_slots1,
+                             double* const* h_peer_scalars2, int world, int rank, int64_t shard_len,
+                             float scaling_norm, int inf_guard, void* workspace, siss_stream_t stream);
+
+int siss_scale_finalize(float* g, int64_t n, const double* scalar_slots1, const double* scalar_slots2, int world,
+                        float scaling_norm, float max_norm, int inf_guard, float* stats5, siss_stream_t stream);
 
 #ifdef __cplusplus
 }

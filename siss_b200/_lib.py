@@ -14,7 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libsiss_b200.so"
 
 SISS_F32, SISS_BF16, SISS_F16 = 0, 1, 2
 SISS_COMBINE_SCALING_NORM, SISS_COMBINE_ERASEDIFF, SISS_COMBINE_NONE = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SissLibraryError(RuntimeError):
@@ -60,6 +60,12 @@ SIGNATURES = {
     "siss_p2p_combine_allgather": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _I, _P, _P]),
     "siss_p2p_adamw_allgather": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _I, _P, _P, _D, _D, _D, _D, _D, _L, _P, _P,
                                       _P, _D, _P, _P]),
+    "siss_nvls_reduce_norm3": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _I, _P, _P]),
+    "siss_nvls_combine_allgather": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _I, _P, _P]),
+    "siss_nvls_adamw_allgather": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _I, _P, _P, _D, _D, _D, _D, _D, _L, _P, _P,
+                                       _P, _D, _P, _P]),
+    "siss_nvls_xcombine_bcast": (_I, [_P, _P, _P, _P, _I, _I, _L, _F, _I, _P, _P]),
+    "siss_scale_finalize": (_I, [_P, _L, _P, _P, _I, _F, _F, _I, _P, _P]),
 }
 
 _lib = None

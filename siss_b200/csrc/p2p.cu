@@ -20,43 +20,17 @@
 // peer pointers. NVLink-bound: per GPU (N-1)/N * 8 B/param inbound for the first kernel,
 // (N-1)/N * 4 B/param outbound for the second.
 
-#include "common.cuh"
-#include "combine_scalars.cuh"
+#include "p2p_common.cuh"
 #include "adam.cuh"
 
 namespace siss {
 
-int cached_sm_count();
-
-constexpr int kP2POcc = 2;
-constexpr int kMaxWorld = 8;
-
-struct P2PWorkspace {
-    unsigned int* counter;
-    double* partials;  // [grid][3]
-};
-constexpr int kP2PMaxGrid = 148 * 4;
-
-inline P2PWorkspace carve_p2p(void* ws) {
-    P2PWorkspace w;
-    w.counter = reinterpret_cast<unsigned int*>(ws);
-    w.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
-    return w;
-}
-
-struct PeerPtrs {
-    const float* x[kMaxWorld];
-    const float* a[kMaxWorld];
-};
-struct PeerOut {
-    float* out[kMaxWorld];
-    double* scalars[kMaxWorld];
-};
-
 // U float4 units per thread per iteration; WORLD x 2 x U 128-bit loads in flight per thread.
-// X_PRE: the G_x shard was already reduced (early reduce-scatter overlapped with the second backward): x is
-// read from the local shard and only G_a crosses NVLink here.
-template <int WORLD, int U, bool X_PRE>
+// XMODE 0: pull G_x and G_a from every peer.
+// XMODE 1: the G_x shard was already reduced (early reduce-scatter overlapped with the second backward): x is
+//          read from the local shard and only G_a crosses NVLink here.
+// XMODE 2: G_a only (first phase of the pipelined exchange, see nvls.cu): x is not touched, sums = {0, Saa, 0}.
+template <int WORLD, int U, int XMODE>
 __global__ void __launch_bounds__(kThreads, kP2POcc)
 p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* elements, % 4 == 0 */,
                         float* shard_x, float* __restrict__ shard_a,
@@ -70,7 +44,7 @@ p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* element
     const long long nchunks = (nvec + chunk - 1) / chunk;
 
     for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        uint4 rx[WORLD][U], ra[WORLD][U];
+        uint4 rx[XMODE == 0 ? WORLD : 1][U], ra[WORLD][U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -84,8 +58,8 @@ p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* element
             for (int u = 0; u < U; ++u) {
                 if (!ok[u]) continue;
                 const long long i = c * chunk + (long long)u * kThreads + threadIdx.x;
-                if (!X_PRE) rx[r][u] = ldg_v4(peers.x[r] + base_elem + 4 * i);
-                else if (r == 0) rx[0][u] = ldg_v4(shard_x + 4 * i);
+                if (XMODE == 0) rx[r][u] = ldg_v4(peers.x[r] + base_elem + 4 * i);
+                else if (XMODE == 1 && r == 0) rx[0][u] = ldg_v4(shard_x + 4 * i);
                 ra[r][u] = ldg_v4(peers.a[r] + base_elem + 4 * i);
             }
         }
@@ -93,59 +67,35 @@ p2p_reduce_norm3_kernel(PeerPtrs peers, int rank, long long shard_len /* element
         for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
             const long long i = c * chunk + (long long)u * kThreads + threadIdx.x;
-            float sx[4], sa[4];
-            VecTraits<float>::unpack(rx[0][u], sx);
+            float sx[4] = {0.f, 0.f, 0.f, 0.f}, sa[4];
+            if (XMODE != 2) VecTraits<float>::unpack(rx[0][u], sx);
             VecTraits<float>::unpack(ra[0][u], sa);
 #pragma unroll
             for (int r = 1; r < WORLD; ++r) {   // fixed rank order
                 float tx[4], ta[4];
-                if (!X_PRE) VecTraits<float>::unpack(rx[r][u], tx);
+                if (XMODE == 0) VecTraits<float>::unpack(rx[r][u], tx);
                 VecTraits<float>::unpack(ra[r][u], ta);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (!X_PRE) sx[q] = __fadd_rn(sx[q], tx[q]);
+                    if (XMODE == 0) sx[q] = __fadd_rn(sx[q], tx[q]);
                     sa[q] = __fadd_rn(sa[q], ta[q]);
                 }
             }
-            if (!X_PRE) stg_stream(shard_x + 4 * i, VecTraits<float>::pack(sx));
+            if (XMODE == 0) stg_stream(shard_x + 4 * i, VecTraits<float>::pack(sx));
             stg_stream(shard_a + 4 * i, VecTraits<float>::pack(sa));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double xd = (double)sx[q], ad = (double)sa[q];
-                acc[0] = fma(xd, xd, acc[0]);
+                if (XMODE != 2) { acc[0] = fma(xd, xd, acc[0]); acc[2] = fma(xd, ad, acc[2]); }
                 acc[1] = fma(ad, ad, acc[1]);
-                acc[2] = fma(xd, ad, acc[2]);
             }
         }
     }
-
-    block_sum<3>(acc, red);
-    if (threadIdx.x == 0) {
-        ws.partials[3 * blockIdx.x + 0] = acc[0];
-        ws.partials[3 * blockIdx.x + 1] = acc[1];
-        ws.partials[3 * blockIdx.x + 2] = acc[2];
-    }
-    if (last_cta_ticket(ws.counter, gridDim.x, &flag)) {
-        if (threadIdx.x < 32) {
-            double t[3] = {0.0, 0.0, 0.0};
-            const volatile double* p = ws.partials;
-            for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) {
-                t[0] += p[3 * b + 0]; t[1] += p[3 * b + 1]; t[2] += p[3 * b + 2];
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) t[k] = warp_sum(t[k]);
-            if (threadIdx.x == 0) { sums3_local[0] = t[0]; sums3_local[1] = t[1]; sums3_local[2] = t[2]; }
-            // publish this rank's partial sums into slot [rank] of every peer (and of itself)
-            if (threadIdx.x < WORLD) {
-                double* dst = pub.scalars[threadIdx.x] + 4 * rank;
-                dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2]; dst[3] = 0.0;
-                __threadfence_system();
-            }
-        }
-    }
+    publish_rank_sums(acc, red, &flag, ws, sums3_local, pub, WORLD, rank);
 }
 
-template <int WORLD, int U>
+// MC: `peers.out[0]` is the MULTICAST address of the output buffer — one multimem.st replaces the WORLD peer stores.
+template <int WORLD, int U, bool MC>
 __global__ void __launch_bounds__(kThreads, kP2POcc)
 p2p_combine_allgather_kernel(const float* __restrict__ shard_x, const float* __restrict__ shard_a,
                              const double* __restrict__ scalar_slots /* [WORLD][4] local */,
@@ -183,9 +133,13 @@ p2p_combine_allgather_kernel(const float* __restrict__ shard_x, const float* __r
             VecTraits<float>::unpack(ra[u], a);
 #pragma unroll
             for (int q = 0; q < 4; ++q) o[q] = __fmul_rn(__fsub_rn(x[q], __fmul_rn(s, a[q])), clip);
-            const uint4 v = VecTraits<float>::pack(o);
+            if (MC) {
+                mc_st_f32x4(peers.out[0] + base_elem + 4 * i, VecTraits<float>::pack(o));                              // all-gather in the switch
+            } else {
+                const uint4 v = VecTraits<float>::pack(o);
 #pragma unroll
-            for (int r = 0; r < WORLD; ++r) stg_stream(peers.out[r] + base_elem + 4 * i, v);  // all-gather by peer stores
+                for (int r = 0; r < WORLD; ++r) stg_stream(peers.out[r] + base_elem + 4 * i, v);  // all-gather by peer stores
+            }
         }
     }
 }
@@ -195,7 +149,7 @@ p2p_combine_allgather_kernel(const float* __restrict__ shard_x, const float* __r
 // to every peer's flat parameter buffer (instead of the combined gradient to every peer's G_x). Same outbound
 // NVLink bytes as p2p_combine_allgather_kernel; the 40 B/param optimiser pass over the full buffer disappears
 // from every rank (it is done once, on 1/WORLD of the parameters, here).
-template <int WORLD, int U, bool EMA>
+template <int WORLD, int U, bool EMA, bool MC>
 __global__ void __launch_bounds__(kThreads, kP2POcc)
 p2p_adamw_allgather_kernel(const float* __restrict__ shard_x, const float* __restrict__ shard_a,
                            const double* __restrict__ scalar_slots, int rank, long long shard_len, PeerOut peers,
@@ -258,21 +212,15 @@ p2p_adamw_allgather_kernel(const float* __restrict__ shard_x, const float* __res
                 for (int q = 0; q < 4; ++q) e[q] = ema_update(e[q], p[q], as.ema_omd);
                 stg_stream(ema + 4 * i, VecTraits<float>::pack(e));
             }
-            const uint4 pv = VecTraits<float>::pack(p);
+            if (MC) {
+                mc_st_f32x4(peers.out[0] + base_elem + 4 * i, VecTraits<float>::pack(p));                               // parameter all-gather (NVLS)
+            } else {
+                const uint4 pv = VecTraits<float>::pack(p);
 #pragma unroll
-            for (int r = 0; r < WORLD; ++r) stg_stream(peers.out[r] + base_elem + 4 * i, pv);  // parameter all-gather
+                for (int r = 0; r < WORLD; ++r) stg_stream(peers.out[r] + base_elem + 4 * i, pv);  // parameter all-gather
+            }
         }
     }
-}
-
-static int p2p_grid(long long nvec, int U) {
-    const long long chunk = (long long)kThreads * U;
-    long long work = (nvec + chunk - 1) / chunk;
-    long long grid = (long long)cached_sm_count() * kP2POcc;
-    if (grid > kP2PMaxGrid) grid = kP2PMaxGrid;
-    if (work < grid) grid = work;
-    if (grid < 1) grid = 1;
-    return (int)grid;
 }
 
 }  // namespace siss
@@ -286,7 +234,9 @@ int64_t siss_p2p_workspace_bytes(void) { return 256 + (int64_t)kP2PMaxGrid * 3 *
 int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_peers_a, double* const* h_peer_scalars,
                           int world, int rank, int64_t shard_len, float* shard_x, float* shard_a,
                           double* sums3_local, int x_prereduced, void* workspace, siss_stream_t stream) {
-    if ((!x_prereduced && !h_peers_x) || !h_peers_a || !h_peer_scalars || !shard_x || !shard_a || !sums3_local || !workspace)
+    if (x_prereduced < 0 || x_prereduced > 2) return SISS_EINVAL;
+    if ((!x_prereduced && !h_peers_x) || !h_peers_a || !h_peer_scalars || (x_prereduced != 2 && !shard_x) || !shard_a ||
+        !sums3_local || !workspace)
         return SISS_EINVAL;
     if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || shard_len < 0 || shard_len % 4 != 0) return SISS_EINVAL;
     PeerPtrs peers{};
@@ -296,17 +246,23 @@ int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_p
         if ((!x_prereduced && !aligned16(h_peers_x[r])) || !aligned16(h_peers_a[r])) return SISS_EINVAL;
         peers.x[r] = x_prereduced ? nullptr : h_peers_x[r]; peers.a[r] = h_peers_a[r]; pub.scalars[r] = h_peer_scalars[r];
     }
-    if (!aligned16(shard_x) || !aligned16(shard_a)) return SISS_EINVAL;
+    if ((x_prereduced != 2 && !aligned16(shard_x)) || !aligned16(shard_a)) return SISS_EINVAL;
     P2PWorkspace ws = carve_p2p(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const long long nvec = shard_len / 4;
 #define SISS_P2P_REDUCE(WORLD_, U_)                                                                                     \
-    if (x_prereduced)                                                                                                  \
-        p2p_reduce_norm3_kernel<WORLD_, U_, true><<<p2p_grid(nvec, U_), kThreads, 0, st>>>(peers, rank, shard_len, shard_x,  \
-                                                                                            shard_a, sums3_local, pub, ws); \
-    else                                                                                                               \
-        p2p_reduce_norm3_kernel<WORLD_, U_, false><<<p2p_grid(nvec, U_), kThreads, 0, st>>>(peers, rank, shard_len, shard_x, \
-                                                                                             shard_a, sums3_local, pub, ws)
+    do {                                                                                                               \
+        const int grid_ = p2p_grid(nvec, U_);                                                                          \
+        if (x_prereduced == 1)                                                                                         \
+            p2p_reduce_norm3_kernel<WORLD_, U_, 1><<<grid_, kThreads, 0, st>>>(peers, rank, shard_len, shard_x, shard_a, \
+                                                                               sums3_local, pub, ws);                  \
+        else if (x_prereduced == 2)                                                                                    \
+            p2p_reduce_norm3_kernel<WORLD_, U_, 2><<<grid_, kThreads, 0, st>>>(peers, rank, shard_len, shard_x, shard_a, \
+                                                                               sums3_local, pub, ws);                  \
+        else                                                                                                           \
+            p2p_reduce_norm3_kernel<WORLD_, U_, 0><<<grid_, kThreads, 0, st>>>(peers, rank, shard_len, shard_x, shard_a, \
+                                                                               sums3_local, pub, ws);                  \
+    } while (0)
     switch (world) {
         case 2: SISS_P2P_REDUCE(2, 4); break;
         case 4: SISS_P2P_REDUCE(4, 2); break;
@@ -314,6 +270,27 @@ int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_p
         default: return SISS_EUNSUPPORTED;  // 2, 4 or 8 GPUs of one NVSwitch box
     }
 #undef SISS_P2P_REDUCE
+    return (int)cudaGetLastError();
+}
+
+static int launch_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                                    const PeerOut& peers, bool mc, int world, int rank, int64_t shard_len, int mode,
+                                    float value, float max_norm, int inf_guard, float* stats5, cudaStream_t st) {
+    const long long nvec = shard_len / 4;
+#define SISS_CAG(WORLD_)                                                                                               \
+    do {                                                                                                               \
+        if (mc) p2p_combine_allgather_kernel<WORLD_, 4, true><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(                 \
+                    shard_x, shard_a, scalar_slots, rank, shard_len, peers, mode, value, max_norm, inf_guard, stats5); \
+        else p2p_combine_allgather_kernel<WORLD_, 4, false><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(                   \
+                    shard_x, shard_a, scalar_slots, rank, shard_len, peers, mode, value, max_norm, inf_guard, stats5); \
+    } while (0)
+    switch (world) {
+        case 2: SISS_CAG(2); break;
+        case 4: SISS_CAG(4); break;
+        case 8: SISS_CAG(8); break;
+        default: return SISS_EUNSUPPORTED;
+    }
+#undef SISS_CAG
     return (int)cudaGetLastError();
 }
 
@@ -329,14 +306,57 @@ int siss_p2p_combine_allgather(const float* shard_x, const float* shard_a, const
         if (!h_peers_out[r] || !aligned16(h_peers_out[r])) return SISS_EINVAL;
         peers.out[r] = h_peers_out[r];
     }
-    cudaStream_t st = (cudaStream_t)stream;
+    return launch_combine_allgather(shard_x, shard_a, scalar_slots, peers, false, world, rank, shard_len, mode, value,
+                                    max_norm, inf_guard, stats5, (cudaStream_t)stream);
+}
+
+int siss_nvls_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                                float* mc_out, int world, int rank, int64_t shard_len,
+                                int mode, float value, float max_norm, int inf_guard, float* stats5,
+                                siss_stream_t stream) {
+    if (!shard_x || !shard_a || !scalar_slots || !mc_out || !aligned16(mc_out)) return SISS_EINVAL;
+    if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || shard_len < 0 || shard_len % 4 != 0) return SISS_EINVAL;
+    if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_NONE) return SISS_EINVAL;
+    PeerOut peers{};
+    peers.out[0] = mc_out;
+    return launch_combine_allgather(shard_x, shard_a, scalar_slots, peers, true, world, rank, shard_len, mode, value,
+                                    max_norm, inf_guard, stats5, (cudaStream_t)stream);
+}
+
+static int launch_adamw_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                                  const PeerOut& peers, bool mc, const float* p_local, int world, int rank,
+                                  int64_t shard_len, int mode, float value, float max_norm, int inf_guard,
+                                  float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                                  double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
+                                  float* ema_shard, double ema_decay, float* stats5, cudaStream_t st) {
+    if (!shard_x || !shard_a || !scalar_slots || !exp_avg || !exp_avg_sq || !p_local) return SISS_EINVAL;
+    if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || shard_len < 0 || shard_len % 4 != 0) return SISS_EINVAL;
+    if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_ERASEDIFF || (step < 1 && !d_step)) return SISS_EINVAL;
+    if (ema_shard && !d_sched && !(ema_decay >= 0.0 && ema_decay <= 1.0)) return SISS_EINVAL;
+    if (!aligned16(shard_x) || !aligned16(shard_a) || !aligned16(exp_avg) || !aligned16(exp_avg_sq) ||
+        !aligned16(ema_shard) || !aligned16(p_local))
+        return SISS_EINVAL;
+    long long hs;
+    const AdamScalars as = make_adam_scalars(lr, beta1, beta2, eps, weight_decay, step, ema_decay, hs);
     const long long nvec = shard_len / 4;
+    const long long* dstep = (const long long*)d_step;
+#define SISS_LAUNCH_P2P_ADAMW(WORLD, EM, MC_)                                                                          \
+    p2p_adamw_allgather_kernel<WORLD, 2, EM, MC_><<<p2p_grid(nvec, 2), kThreads, 0, st>>>(                              \
+        shard_x, shard_a, scalar_slots, rank, shard_len, peers, p_local, exp_avg, exp_avg_sq, ema_shard, as, hs, dstep, \
+        d_sched, mode, value, max_norm, inf_guard, stats5)
+#define SISS_ADAMW_WORLD(WORLD)                                                                                        \
+    do {                                                                                                               \
+        if (ema_shard) { if (mc) SISS_LAUNCH_P2P_ADAMW(WORLD, true, true); else SISS_LAUNCH_P2P_ADAMW(WORLD, true, false); }   \
+        else           { if (mc) SISS_LAUNCH_P2P_ADAMW(WORLD, false, true); else SISS_LAUNCH_P2P_ADAMW(WORLD, false, false); } \
+    } while (0)
     switch (world) {
-        case 2: p2p_combine_allgather_kernel<2, 4><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(shard_x, shard_a, scalar_slots, rank, shard_len, peers, mode, value, max_norm, inf_guard, stats5); break;
-        case 4: p2p_combine_allgather_kernel<4, 4><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(shard_x, shard_a, scalar_slots, rank, shard_len, peers, mode, value, max_norm, inf_guard, stats5); break;
-        case 8: p2p_combine_allgather_kernel<8, 4><<<p2p_grid(nvec, 4), kThreads, 0, st>>>(shard_x, shard_a, scalar_slots, rank, shard_len, peers, mode, value, max_norm, inf_guard, stats5); break;
+        case 2: SISS_ADAMW_WORLD(2); break;
+        case 4: SISS_ADAMW_WORLD(4); break;
+        case 8: SISS_ADAMW_WORLD(8); break;
         default: return SISS_EUNSUPPORTED;
     }
+#undef SISS_ADAMW_WORLD
+#undef SISS_LAUNCH_P2P_ADAMW
     return (int)cudaGetLastError();
 }
 
@@ -346,35 +366,32 @@ int siss_p2p_adamw_allgather(const float* shard_x, const float* shard_a, const d
                              float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
                              double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
                              float* ema_shard, double ema_decay, float* stats5, siss_stream_t stream) {
-    if (!shard_x || !shard_a || !scalar_slots || !h_peers_param || !exp_avg || !exp_avg_sq) return SISS_EINVAL;
-    if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || shard_len < 0 || shard_len % 4 != 0) return SISS_EINVAL;
-    if (mode < SISS_COMBINE_SCALING_NORM || mode > SISS_COMBINE_ERASEDIFF || (step < 1 && !d_step)) return SISS_EINVAL;
-    if (ema_shard && !d_sched && !(ema_decay >= 0.0 && ema_decay <= 1.0)) return SISS_EINVAL;
-    if (!aligned16(shard_x) || !aligned16(shard_a) || !aligned16(exp_avg) || !aligned16(exp_avg_sq) || !aligned16(ema_shard))
-        return SISS_EINVAL;
+    if (!h_peers_param || world < 2 || world > kMaxWorld || rank < 0 || rank >= world) return SISS_EINVAL;
     PeerOut peers{};
     for (int r = 0; r < world; ++r) {
         if (!h_peers_param[r] || !aligned16(h_peers_param[r])) return SISS_EINVAL;
         peers.out[r] = h_peers_param[r];
     }
-    long long hs;
-    const AdamScalars as = make_adam_scalars(lr, beta1, beta2, eps, weight_decay, step, ema_decay, hs);
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long nvec = shard_len / 4;
-    const long long* dstep = (const long long*)d_step;
-#define SISS_LAUNCH_P2P_ADAMW(WORLD, EM)                                                                               \
-    p2p_adamw_allgather_kernel<WORLD, 2, EM><<<p2p_grid(nvec, 2), kThreads, 0, st>>>(                                   \
-        shard_x, shard_a, scalar_slots, rank, shard_len, peers, h_peers_param[rank] + (long long)rank * shard_len,     \
-        exp_avg, exp_avg_sq, ema_shard, as, hs, dstep, d_sched,                                                       \
-        mode, value, max_norm, inf_guard, stats5)
-    switch (world) {
-        case 2: if (ema_shard) SISS_LAUNCH_P2P_ADAMW(2, true); else SISS_LAUNCH_P2P_ADAMW(2, false); break;
-        case 4: if (ema_shard) SISS_LAUNCH_P2P_ADAMW(4, true); else SISS_LAUNCH_P2P_ADAMW(4, false); break;
-        case 8: if (ema_shard) SISS_LAUNCH_P2P_ADAMW(8, true); else SISS_LAUNCH_P2P_ADAMW(8, false); break;
-        default: return SISS_EUNSUPPORTED;
-    }
-#undef SISS_LAUNCH_P2P_ADAMW
-    return (int)cudaGetLastError();
+    return launch_adamw_allgather(shard_x, shard_a, scalar_slots, peers, false,
+                                  h_peers_param[rank] + (long long)rank * shard_len, world, rank, shard_len, mode, value,
+                                  max_norm, inf_guard, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step,
+                                  d_step, d_sched, ema_shard, ema_decay, stats5, (cudaStream_t)stream);
+}
+
+int siss_nvls_adamw_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                              float* mc_param, const float* param_local, int world, int rank, int64_t shard_len,
+                              int mode, float value, float max_norm, int inf_guard,
+                              float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                              double weight_decay, int64_t step, const int64_t* d_step, const double* d_sched,
+                              float* ema_shard, double ema_decay, float* stats5, siss_stream_t stream) {
+    if (!mc_param || !aligned16(mc_param) || !param_local || world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
+        return SISS_EINVAL;
+    PeerOut peers{};
+    peers.out[0] = mc_param;
+    return launch_adamw_allgather(shard_x, shard_a, scalar_slots, peers, true, param_local + (long long)rank * shard_len,
+                                  world, rank, shard_len, mode, value, max_norm, inf_guard, exp_avg, exp_avg_sq, lr, beta1,
+                                  beta2, eps, weight_decay, step, d_step, d_sched, ema_shard, ema_decay, stats5,
+                                  (cudaStream_t)stream);
 }
 
 }  // extern "C"

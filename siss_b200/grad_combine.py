@@ -71,16 +71,18 @@ class GradCombiner:
         quantum = _ALIGN * self.world
         self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's shard is 16B aligned
         self.peer = None
-        if transport not in ("auto", "p2p", "nccl"):
+        self.tuning = {}
+        peer_names = ("p2p", "nvls", "pipe", "pipe_nvls")
+        if transport not in ("auto", "nccl") + peer_names:
             raise ValueError(f"unknown transport {transport!r}")
-        want_p2p = transport == "p2p" or (transport == "auto" and self.world in (2, 4))
-        if self.world > 1 and want_p2p and dev.type == "cuda":
+        want_peer = transport != "nccl"
+        if self.world > 1 and want_peer and dev.type == "cuda" and self.world in (2, 4, 8):
             err = None
             try:
                 from .p2p import PeerExchange
                 self.peer = PeerExchange(self.total, dev, process_group)
             except Exception as e:
-                if transport == "p2p":
+                if transport != "auto":
                     raise
                 err = e
                 self.peer = None
@@ -89,17 +91,27 @@ class GradCombiner:
             ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
             if int(ok.item()) == 0:
-                if self.peer is not None or err is not None:
-                    import warnings
-                    warnings.warn("siss_b200: peer-memory transport unavailable on at least one rank "
-                                  f"({err!r}); every rank uses NCCL collectives")
+                if transport != "auto":
+                    raise RuntimeError(f"transport {transport!r} could not be set up on every rank ({err!r})")
+                import warnings
+                warnings.warn("siss_b200: peer-memory transport unavailable on at least one rank "
+                              f"({err!r}); every rank uses NCCL collectives")
                 self.peer = None
+            elif transport != "auto":
+                if transport not in self.peer.available():
+                    raise RuntimeError(f"transport {transport!r} needs NVSwitch multicast, which this node does not provide")
+                self.peer.algo = transport
+                three = transport if transport in ("p2p", "nvls") else ("nvls" if transport == "pipe_nvls" else "p2p")
+                self.peer.algo3 = self.peer.algo_xpre = three
+        elif self.world > 1 and transport in peer_names:
+            raise RuntimeError(f"transport {transport!r} needs CUDA and 2, 4 or 8 ranks on one node")
         if self.peer is not None:
             self.g_x, self.g_a = self.peer.g_x, self.peer.g_a
         else:
             self.g_x = torch.zeros(self.total, dtype=torch.float32, device=dev)
             self.g_a = torch.zeros(self.total, dtype=torch.float32, device=dev)
-        self.transport = "single" if self.world == 1 else ("p2p" if self.peer is not None else "nccl")
+        self.transport = "single" if self.world == 1 else (self.peer.algo if self.peer is not None else "nccl")
+        self._nccl_full = self._nccl_xpre = self.peer is None     # which situations go through NCCL collectives
         self._views_x = [self.g_x[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
         self._views_a = [self.g_a[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
         self.sums3 = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -119,7 +131,43 @@ class GradCombiner:
         # replace these two attributes with the oracle; the product has no other path.)
         self._norm3 = ops.norm3
         self._combine = ops.combine
+        if self.world > 1 and transport == "auto" and self.peer is not None:
+            self._autotune()
         self._point(self._views_x)   # start out accumulating into G_x (needed by the after_backward_* spelling)
+
+    # ------------------------------------------------------------------------------------------
+    def _nccl_exchange(self, mode: int, value: float, mn: float, inf_guard: bool, x_prereduced: bool) -> None:
+        """The exchange as torch.distributed collectives around K4a / K4b: reduce-scatter G_x and G_a (ONE grouped
+        NCCL launch), K4a on the 1/N shard, all-reduce of the three fp64 scalars, K4b on the shard, all-gather."""
+        if x_prereduced:
+            dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
+        elif self.device.type == "cuda":
+            # one grouped NCCL launch (ncclGroupStart/End) for both buffers instead of two serialised collectives
+            with dist._coalescing_manager(group=self.group, async_ops=False):
+                dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+                dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+            dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
+        self._norm3(self._shard_x, self._shard_a, out=self.sums3)
+        dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)  # the scalar-norm all-reduce
+        self._combine(self._shard_x, self._shard_a, self.sums3, mode, value, mn, inf_guard, out=self._shard_x,
+                      stats=self.stats)
+        dist.all_gather_into_tensor(self.g_x, self._shard_x, group=self.group)
+
+    def _autotune(self) -> None:
+        """transport="auto": time every schedule of the peer / multicast kernels AND the NCCL collectives on the real
+        buffers (max over ranks, so every rank takes the same decision) and keep the fastest — separately for the full
+        exchange and for the exchange whose G_x shard was reduced early. Results stay in ``self.tuning``."""
+        res = self.peer.tune(extra={"nccl": lambda xpre: self._nccl_exchange(SISS_COMBINE_SCALING_NORM, 500.0, 1.0,
+                                                                             False, xpre)})
+        self.tuning = res
+        best_peer_full = res.get(self.peer.algo, float("inf"))
+        best_peer_xpre = res.get(self.peer.algo_xpre + "+xpre", float("inf"))
+        self._nccl_full = res.get("nccl", float("inf")) < best_peer_full
+        self._nccl_xpre = res.get("nccl+xpre", float("inf")) < best_peer_xpre
+        self.transport = "nccl" if self._nccl_full else self.peer.algo
+        self.stats.zero_()
 
     # ------------------------------------------------------------------------------------------
     def _point(self, views: List[torch.Tensor]) -> None:
@@ -192,26 +240,46 @@ class GradCombiner:
         if self.world == 1:
             self._norm3(self.g_x, self.g_a, out=self.sums3)
             self._combine(self.g_x, self.g_a, self.sums3, mode, value, mn, inf_guard, out=self.g_x, stats=self.stats)
-        elif self.peer is not None:
-            if self._early_x:
-                torch.cuda.current_stream(self.device).wait_event(self._early_done)
-            self.peer.combine(mode, value, mn, inf_guard, self.stats, x_prereduced=self._early_x)
         else:
-            if self._early_x:
-                torch.cuda.current_stream(self.device).wait_event(self._early_done)
-            else:
-                dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
-            dist.reduce_scatter_tensor(self._shard_a, self.g_a, op=dist.ReduceOp.SUM, group=self.group)
-            self._norm3(self._shard_x, self._shard_a, out=self.sums3)
-            dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)  # the scalar-norm all-reduce
-            self._combine(self._shard_x, self._shard_a, self.sums3, mode, value, mn, inf_guard, out=self._shard_x,
-                          stats=self.stats)
-            dist.all_gather_into_tensor(self.g_x, self._shard_x, group=self.group)
+            self.exchange(mode, value, mn, inf_guard)
         self.g_a.zero_()
         self._dirty_x = True
         self._early_x = False
         self._point(self._views_x)
         return self.stats
+
+    def exchange(self, mode: int, value: float, max_norm: float, inf_guard: bool = False) -> torch.Tensor:
+        """Data parallel only — the exchange step by itself: sum ``G_x`` / ``G_a`` over the ranks, K4a, K4b, result in
+        every rank's ``G_x``; through whichever transport was chosen (fused peer / multicast kernels or NCCL collectives).
+        Does NOT clear ``G_a`` or touch ``param.grad`` (that is :meth:`combine`). Returns the device stats tensor."""
+        if self.world == 1:
+            raise RuntimeError("exchange() is a data-parallel step")
+        if self._early_x:
+            torch.cuda.current_stream(self.device).wait_event(self._early_done)
+        use_nccl = self._nccl_xpre if self._early_x else self._nccl_full
+        if use_nccl:
+            self._nccl_exchange(mode, value, max_norm, inf_guard, self._early_x)
+        else:
+            self.peer.combine(mode, value, max_norm, inf_guard, self.stats, x_prereduced=self._early_x)
+        return self.stats
+
+    def wire_bytes(self, x_prereduced: bool = False) -> Dict[str, object]:
+        """Bytes that cross this GPU's NVLink ports in one exchange, per direction, for the schedule in use (P = padded
+        parameter count, S = P / N; the switch fetches a multicast reduce from ALL N replicas, the requester's included)."""
+        N, P4 = self.world, 4 * self.total
+        S4 = P4 // max(N, 1)
+        name = "nccl" if (self._nccl_xpre if x_prereduced else self._nccl_full) else \
+            (self.peer.algo_xpre if x_prereduced else self.peer.algo)
+        nx = 0 if x_prereduced else 1
+        if name in ("p2p", "nccl"):          # NCCL: ring-equivalent count (its NVLS path is internal to the library)
+            out = inb = (N - 1) * S4 * (1 + nx) + (N - 1) * S4
+        elif name == "nvls":
+            out, inb = P4 * (1 + nx) + S4, S4 * (1 + nx) + P4
+        elif name == "pipe":
+            out, inb = (N - 1) * S4 + P4 + S4, (N - 1) * S4 + S4 + P4
+        else:                                # pipe_nvls
+            out, inb = P4 + P4 + S4, S4 + S4 + P4
+        return {"schedule": name, "out_bytes": int(out), "in_bytes": int(inb)}
 
     def reduce_to_shards(self, single_term: bool = False) -> torch.Tensor:
         """Data parallel only — the first half of the exchange: reduce-scatter the gradient buffer(s) into this rank's

@@ -54,13 +54,13 @@ class FusedCombineAdamW:
             float(weight_decay)
         dev = combiner.device
         if shard_optimizer is None:
-            # NCCL transport: always. Peer-memory transport: the fused parameter all-gather kernel is validated
-            # against the replicated update at 2 and 4 ranks (tests/test_distributed_gpu.py); 8 ranks opt in explicitly
-            # (transport "auto" picks NCCL there anyway).
-            shard_optimizer = combiner.world > 1 and (combiner.peer is None or combiner.world in (2, 4))
+            # every data-parallel run: the update is done once, on 1/N of the parameters (N ranks == 1 rank tested at
+            # 2, 4 and 8 ranks for the NCCL, peer-memory and multicast transports, tests/test_distributed_gpu.py)
+            shard_optimizer = combiner.world > 1
         self.sharded = bool(shard_optimizer) and combiner.world > 1
-        # sharded + peer-memory transport: parameters live in symmetric memory, gathered by peer stores
-        self.fused_gather = self.sharded and combiner.peer is not None
+        # sharded + peer / multicast transport: parameters live in symmetric memory and are gathered by the fused kernel
+        # (peer stores or one multicast store per vector) — unless the start-up measurement found NCCL faster
+        self.fused_gather = self.sharded and combiner.peer is not None and not combiner._nccl_xpre
         self.p_flat = combiner.peer.alloc_params() if self.fused_gather else \
             torch.zeros(combiner.total, dtype=torch.float32, device=dev)
         for p, off in zip(combiner.params, combiner.offsets):

@@ -1,23 +1,39 @@
-"""NVLink peer-memory transport for the data-parallel gradient combine.
+"""NVLink transports for the data-parallel gradient combine: peer memory and NVSwitch multicast (NVLS).
 
 ``G_x`` and ``G_a`` live in symmetric memory (``torch.distributed._symmetric_memory``: every rank's
-allocation is mapped into every process of the node), and the exchange + K4 run as two fused kernels of
-libsiss_b200.so (csrc/p2p.cu) instead of five NCCL collectives around two kernels:
+allocation is mapped into every process of the node, and — on an NVSwitch box — bound to one multicast
+address), and the exchange + K4 run as fused kernels of libsiss_b200.so (csrc/p2p.cu, csrc/nvls.cu)
+instead of five NCCL collectives around two kernels. Four schedules (``algo``):
 
-    barrier | siss_p2p_reduce_norm3 (reduce-scatter x2 + K4a, peer loads) | barrier
-            | siss_p2p_combine_allgather (K4b + all-gather, peer stores)  | barrier
+  "p2p"        barrier | siss_p2p_reduce_norm3 (reduce-scatter x2 + K4a, peer loads)   | barrier
+                       | siss_p2p_combine_allgather (K4b + all-gather, peer stores)    | barrier
+  "nvls"       the same three stages with multimem.ld_reduce / multimem.st (reduction and replication
+               inside the switch: 8 + 4/N bytes per parameter outbound, 4 + 8/N inbound)
+  "pipe"       pipelined, scaling-norm modes only (csrc/nvls.cu): G_a reduce (peer loads) | barrier |
+               ONE kernel that reduces G_x in the switch, forms x - s a and replicates it in place
+               (reduce traffic outbound and gather traffic inbound at the same time) | barrier |
+               local clip pass
+  "pipe_nvls"  as "pipe" with the G_a reduce through the switch as well
 
-torch is plumbing here: allocation, rendezvous (pointer exchange) and the stream-ordered barriers.
+Which one is fastest depends on the rank count (the in-switch forms move more bytes at N = 2 and fewer
+at N = 8), so :meth:`PeerExchange.tune` measures them on the real buffers at start-up and the choice is
+made collectively (max over ranks). torch is plumbing here: allocation, rendezvous (pointer exchange),
+multicast binding and the stream-ordered barriers.
 """
 from __future__ import annotations
 
 import ctypes
-from typing import Optional
+from typing import Callable, Dict, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
+from ._lib import SISS_COMBINE_SCALING_NORM
+
+THREE_STAGE = ("p2p", "nvls")
+PIPELINED = ("pipe", "pipe_nvls")
+ALGOS = THREE_STAGE + PIPELINED
 
 
 class PeerExchange:
@@ -35,7 +51,9 @@ class PeerExchange:
         f32, f64 = torch.float32, torch.float64
         self.g_x = symm_mem.empty(total, dtype=f32, device=device)
         self.g_a = symm_mem.empty(total, dtype=f32, device=device)
-        self.scalars = symm_mem.empty(4 * self.world, dtype=f64, device=device)
+        # two slot arrays of [world][4] doubles: per-rank partial sums of the reduce kernel, and (pipelined
+        # schedule) of the x-combine kernel
+        self.scalars = symm_mem.empty(8 * self.world, dtype=f64, device=device)
         self.g_x.zero_(); self.g_a.zero_(); self.scalars.zero_()
         self.h_x = symm_mem.rendezvous(self.g_x, self.group)
         self.h_a = symm_mem.rendezvous(self.g_a, self.group)
@@ -44,73 +62,193 @@ class PeerExchange:
         self.ptrs_x = arr(*[int(p) for p in self.h_x.buffer_ptrs])
         self.ptrs_a = arr(*[int(p) for p in self.h_a.buffer_ptrs])
         self.ptrs_s = arr(*[int(p) for p in self.h_s.buffer_ptrs])
+        self.ptrs_s2 = arr(*[int(p) + 4 * self.world * 8 for p in self.h_s.buffer_ptrs])
         assert int(self.ptrs_x[self.rank]) == self.g_x.data_ptr(), "symmetric-memory pointer table does not match"
+        self.slots1 = self.scalars[:4 * self.world]
+        self.slots2 = self.scalars[4 * self.world:]
+        # multicast (NVLS) addresses of the two gradient buffers; 0 when the fabric / driver has none
+        self.mc_x = int(getattr(self.h_x, "multicast_ptr", 0) or 0)
+        self.mc_a = int(getattr(self.h_a, "multicast_ptr", 0) or 0)
+        self.mc_p = 0
+        self.has_multicast = bool(self.mc_x and self.mc_a)
         self.shard_x = torch.empty(self.shard_len, dtype=f32, device=device)
         self.shard_a = torch.empty(self.shard_len, dtype=f32, device=device)
         self.sums_local = torch.zeros(3, dtype=f64, device=device)
         self.ws = torch.zeros(_lib.load().siss_p2p_workspace_bytes(), dtype=torch.uint8, device=device)
+        self.algo = "p2p"          # schedule used when combine() is not told otherwise (see tune())
+        self.algo_xpre = "p2p"     # ... when G_x arrives already reduced (three-stage schedules only)
+        self.algo3 = "p2p"         # ... best three-stage schedule of the full exchange (EraseDiff cannot be pipelined)
+        self.tuning: Dict[str, float] = {}
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)
 
+    # ------------------------------------------------------------------------------------------
+    def available(self) -> Sequence[str]:
+        return ALGOS if self.has_multicast else ("p2p",)
+
+    def _resolve(self, algo: Optional[str], mode: int, x_prereduced: bool) -> str:
+        if x_prereduced:
+            algo = algo if algo in THREE_STAGE else self.algo_xpre
+        elif algo is None:
+            algo = self.algo
+        if algo in PIPELINED and (mode != SISS_COMBINE_SCALING_NORM or x_prereduced):
+            # EraseDiff's s needs <G_x, G_a>; a prereduced G_x makes the three sums available after the first kernel
+            algo = self.algo_xpre if x_prereduced else self.algo3
+        if algo not in ALGOS:
+            raise ValueError(f"unknown exchange schedule {algo!r}")
+        if algo != "p2p" and not self.has_multicast:
+            raise RuntimeError(f"schedule {algo!r} needs a multicast (NVLS) binding, which this node does not provide")
+        return algo
+
     def alloc_params(self) -> torch.Tensor:
         """Flat fp32 parameter buffer in symmetric memory (same length as G_x), for the sharded optimiser step whose
-        parameter all-gather is done by peer stores (:meth:`adamw_allgather`). Collective: call on every rank."""
+        parameter all-gather is done by peer stores / multicast stores (:meth:`adamw_allgather`). Collective."""
         import torch.distributed._symmetric_memory as symm_mem
         self.p_flat = symm_mem.empty(self.total, dtype=torch.float32, device=self.g_x.device)
         self.p_flat.zero_()
         self.h_p = symm_mem.rendezvous(self.p_flat, self.group)
         self.ptrs_p = (ctypes.c_void_p * self.world)(*[int(p) for p in self.h_p.buffer_ptrs])
         assert int(self.ptrs_p[self.rank]) == self.p_flat.data_ptr(), "symmetric-memory pointer table does not match"
+        self.mc_p = int(getattr(self.h_p, "multicast_ptr", 0) or 0)
         torch.cuda.synchronize(self.g_x.device)
         dist.barrier(group=self.group)
         return self.p_flat
 
+    # ------------------------------------------------------------------------------------------
+    def _reduce(self, lib, stream, algo: str, x_mode: int) -> None:
+        P = ctypes.c_void_p
+        if algo == "nvls":
+            _lib.check(lib.siss_nvls_reduce_norm3(P(self.mc_x), P(self.mc_a), self.ptrs_s, self.world, self.rank,
+                                                  self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
+                                                  self.sums_local.data_ptr(), x_mode, self.ws.data_ptr(), stream),
+                       "siss_nvls_reduce_norm3")
+        else:
+            _lib.check(lib.siss_p2p_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
+                                                 self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
+                                                 self.sums_local.data_ptr(), x_mode, self.ws.data_ptr(), stream),
+                       "siss_p2p_reduce_norm3")
+
     def adamw_allgather(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
                         exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, ema_shard: Optional[torch.Tensor],
                         lr: float, betas, eps: float, weight_decay: float, step: int, d_step: torch.Tensor,
-                        d_sched: Optional[torch.Tensor], ema_decay: float, x_prereduced: bool = False) -> None:
-        """Two-term sync step with the ZeRO-1 update: reduce kernel as in :meth:`combine`, then
-        ``siss_p2p_adamw_allgather`` (K4b + AdamW/EMA on this rank's shard + parameter all-gather by peer stores).
-        New parameters land in every rank's ``p_flat``. Stream-ordered; no host synchronisation."""
+                        d_sched: Optional[torch.Tensor], ema_decay: float, x_prereduced: bool = False,
+                        algo: Optional[str] = None) -> None:
+        """Two-term sync step with the ZeRO-1 update: reduce kernel as in :meth:`combine`, then K4b + AdamW/EMA on this
+        rank's shard + parameter all-gather (peer stores or one multicast store per vector). New parameters land in
+        every rank's ``p_flat``. Three-stage schedules only. Stream-ordered; no host synchronisation."""
         from . import ops
         lib = _lib.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = ctypes.c_void_p
+        algo = algo if algo in THREE_STAGE else (self.algo_xpre if x_prereduced else self.algo3)
+        if algo == "nvls" and not (self.has_multicast and self.mc_p):
+            algo = "p2p"
         self.h_x.barrier(channel=0)
-        _lib.check(lib.siss_p2p_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
-                                             self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                             self.sums_local.data_ptr(), int(bool(x_prereduced)), self.ws.data_ptr(),
-                                             stream), "siss_p2p_reduce_norm3")
+        self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
         self.h_x.barrier(channel=1)
-        _lib.check(lib.siss_p2p_adamw_allgather(
-            self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), self.ptrs_p, self.world,
-            self.rank, self.shard_len, int(mode), float(value), float(max_norm), int(bool(inf_guard)),
-            P(exp_avg.data_ptr()), P(exp_avg_sq.data_ptr()), float(lr), float(betas[0]), float(betas[1]), float(eps),
-            float(weight_decay), int(step), P(d_step.data_ptr()), P(0 if d_sched is None else d_sched.data_ptr()),
-            P(0 if ema_shard is None else ema_shard.data_ptr()), float(ema_decay), P(stats.data_ptr()), stream),
-            "siss_p2p_adamw_allgather")
+        tail = (int(mode), float(value), float(max_norm), int(bool(inf_guard)),
+                P(exp_avg.data_ptr()), P(exp_avg_sq.data_ptr()), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                float(weight_decay), int(step), P(d_step.data_ptr()), P(0 if d_sched is None else d_sched.data_ptr()),
+                P(0 if ema_shard is None else ema_shard.data_ptr()), float(ema_decay), P(stats.data_ptr()), stream)
+        if algo == "nvls":
+            _lib.check(lib.siss_nvls_adamw_allgather(
+                self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), P(self.mc_p),
+                P(self.p_flat.data_ptr()), self.world, self.rank, self.shard_len, *tail), "siss_nvls_adamw_allgather")
+        else:
+            _lib.check(lib.siss_p2p_adamw_allgather(
+                self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), self.ptrs_p, self.world,
+                self.rank, self.shard_len, *tail), "siss_p2p_adamw_allgather")
         self.h_x.barrier(channel=2)        # every rank's parameter shard has landed in every p_flat
         ops._count(2)
 
     def combine(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
-                x_prereduced: bool = False) -> None:
-        """Result lands in every rank's ``g_x``. Stream-ordered; no host synchronisation. With
-        ``x_prereduced`` the reduced ``G_x`` shard is already in ``shard_x`` (early reduce-scatter overlapped
-        with the second backward) and only ``G_a`` crosses NVLink in the first kernel."""
+                x_prereduced: bool = False, algo: Optional[str] = None) -> None:
+        """Result lands in every rank's ``g_x``. Stream-ordered; no host synchronisation. With ``x_prereduced`` the
+        reduced ``G_x`` shard is already in ``shard_x`` (early reduce-scatter overlapped with the second backward) and
+        only ``G_a`` crosses NVLink in the first kernel. ``algo`` overrides the tuned schedule."""
         from . import ops
         lib = _lib.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = ctypes.c_void_p
+        algo = self._resolve(algo, int(mode), bool(x_prereduced))
+        mn, ig = float(max_norm), int(bool(inf_guard))
         self.h_x.barrier(channel=0)        # every rank's G_x / G_a are complete
-        _lib.check(lib.siss_p2p_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
-                                             self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                             self.sums_local.data_ptr(), int(bool(x_prereduced)), self.ws.data_ptr(),
-                                             stream),
-                   "siss_p2p_reduce_norm3")
+        if algo in PIPELINED:
+            self._reduce(lib, stream, "nvls" if algo == "pipe_nvls" else "p2p", 2)          # phase 1: G_a, sum a^2
+            self.h_x.barrier(channel=1)    # every rank's sum a^2 is in every slot array
+            _lib.check(lib.siss_nvls_xcombine_bcast(P(self.mc_x), self.shard_a.data_ptr(), self.slots1.data_ptr(),
+                                                    self.ptrs_s2, self.world, self.rank, self.shard_len, float(value),
+                                                    ig, self.ws.data_ptr(), stream), "siss_nvls_xcombine_bcast")
+            self.h_x.barrier(channel=2)    # unclipped combination complete in every G_x; second slot array filled
+            _lib.check(lib.siss_scale_finalize(self.g_x.data_ptr(), self.total, self.slots1.data_ptr(),
+                                               self.slots2.data_ptr(), self.world, float(value), mn, ig,
+                                               stats.data_ptr(), stream), "siss_scale_finalize")
+            ops._count(3)
+            return
+        self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
         self.h_x.barrier(channel=1)        # every rank's scalar slot has been written everywhere
-        _lib.check(lib.siss_p2p_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                                  self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
-                                                  self.shard_len, int(mode), float(value), float(max_norm),
-                                                  int(bool(inf_guard)), stats.data_ptr(), stream),
-                   "siss_p2p_combine_allgather")
+        if algo == "nvls":
+            _lib.check(lib.siss_nvls_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
+                                                       self.scalars.data_ptr(), P(self.mc_x), self.world, self.rank,
+                                                       self.shard_len, int(mode), float(value), mn, ig,
+                                                       stats.data_ptr(), stream), "siss_nvls_combine_allgather")
+        else:
+            _lib.check(lib.siss_p2p_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
+                                                      self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
+                                                      self.shard_len, int(mode), float(value), mn, ig,
+                                                      stats.data_ptr(), stream), "siss_p2p_combine_allgather")
         self.h_x.barrier(channel=2)        # every rank's shard of the result has landed in every G_x
         ops._count(2)
+
+    # ------------------------------------------------------------------------------------------
+    def tune(self, extra: Optional[Dict[str, Callable[[bool], None]]] = None, iters: int = 4,
+             candidates: Optional[Sequence[str]] = None) -> Dict[str, float]:
+        """Measure every available schedule on the real buffers (CUDA events, max over ranks) and adopt the fastest
+        for (a) the full exchange and (b) the exchange with G_x already reduced. ``extra`` adds competitors that are
+        not schedules of this class — e.g. ``{"nccl": fn}`` with ``fn(x_prereduced)`` running the NCCL collectives —
+        so that the caller can pick between transports with the same clock. Collective: every rank must call it with
+        the same arguments; the decision is taken on all-reduced (MAX) timings and is therefore identical everywhere.
+        Overwrites the gradient buffers (call before the first backward). Returns {name: ms}; the winners are stored in
+        ``algo`` / ``algo_xpre`` (names from ``extra`` are reported but not stored)."""
+        dev = self.g_x.device
+        stats = torch.zeros(5, dtype=torch.float32, device=dev)
+        names = [a for a in (candidates or self.available()) if a in self.available()]
+        runs = []
+        for a in names:
+            runs.append((a, (lambda a=a: self.combine(SISS_COMBINE_SCALING_NORM, 500.0, 1.0, False, stats, algo=a))))
+            if a in THREE_STAGE:
+                runs.append((a + "+xpre", (lambda a=a: self.combine(SISS_COMBINE_SCALING_NORM, 500.0, 1.0, False, stats,
+                                                                    x_prereduced=True, algo=a))))
+        for k, fn in (extra or {}).items():
+            runs.append((k, (lambda fn=fn: fn(False))))
+            runs.append((k + "+xpre", (lambda fn=fn: fn(True))))
+        times = torch.zeros(len(runs), dtype=torch.float64, device=dev)
+        for j, (_, fn) in enumerate(runs):
+            # non-trivial values: zeros would make s infinite and let the clip pass of the pipelined schedule exit early
+            self.g_x.fill_(1e-3); self.g_a.fill_(1e-3); self.shard_x.fill_(1e-3)
+            fn()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                fn()
+            e.record()
+            torch.cuda.synchronize(dev)
+            times[j] = s.elapsed_time(e) / iters
+        dist.all_reduce(times, op=dist.ReduceOp.MAX, group=self.group)
+        self.g_x.zero_(); self.g_a.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+        res = {name: float(t) for (name, _), t in zip(runs, times.tolist())}
+        own_full = {k: v for k, v in res.items() if k in ALGOS}
+        own_xpre = {k[:-5]: v for k, v in res.items() if k.endswith("+xpre") and k[:-5] in THREE_STAGE}
+        if own_full:
+            self.algo = min(own_full, key=own_full.get)
+            three = {k: v for k, v in own_full.items() if k in THREE_STAGE}
+            if three:
+                self.algo3 = min(three, key=three.get)
+        if own_xpre:
+            self.algo_xpre = min(own_xpre, key=own_xpre.get)
+        self.tuning = res
+        return res

@@ -47,8 +47,9 @@ def _run_opt(rank, world, Bg, transport="auto", shard=None):
     opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, ema=dict(decay=0.9),
                             shard_optimizer=shard)
     if world > 1:
-        assert opt.sharded == ((transport == "nccl" or world in (2, 4)) if shard is None else shard)
-        assert opt.fused_gather == (opt.sharded and transport == "p2p")      # parameter all-gather by peer stores
+        assert opt.sharded == (True if shard is None else shard)
+        # parameter all-gather inside the fused kernel (peer stores / multicast stores) whenever a peer transport is in use
+        assert opt.fused_gather == (opt.sharded and comb.peer is not None and not comb._nccl_xpre)
         if opt.sharded:
             assert opt.exp_avg.numel() == comb.total // world and opt.ema_flat.numel() == comb.total // world
     step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
@@ -102,10 +103,14 @@ def _worker(rank, world, port, q):
     from siss_b200 import parallel
     parallel.init_from_env("nccl")
     out = {}
-    for transport in ("nccl", "p2p"):
+    from siss_b200.grad_combine import GradCombiner
+    probe = GradCombiner(TinyNet().to(torch.device("cuda", rank)).parameters(), transport="p2p")
+    multicast = probe.peer.has_multicast            # NVSwitch multicast bound: the in-switch schedules exist too
+    del probe
+    for transport in ("nccl", "p2p", "auto") + (("nvls", "pipe", "pipe_nvls") if multicast else ()):
         out[transport] = _run(rank, world, 8, 2, transport)
-        if world in (2, 4):
-            out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
+        out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
+        if transport in ("nccl", "p2p"):
             out[transport + "/fused_adamw_replicated"] = _run_opt(rank, world, 8, transport, shard=False)
     if rank == 0:
         q.put(out)
@@ -128,7 +133,7 @@ def test_multi_gpu_step_equals_single_gpu(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     flat1, stats1 = _run(0, 1, 8, 2)
-    params1 = _run_opt(0, 1, 8) if world in (2, 4) else None
+    params1 = _run_opt(0, 1, 8)
     for transport, res in out.items():                  # NCCL collectives and fused NVLink peer-memory kernels
         if "/fused_adamw" in transport:                 # replicated and ZeRO-1 sharded layouts, parameters + EMA shadow
             torch.testing.assert_close(res, params1, rtol=3e-5, atol=3e-6, msg=lambda m: f"{transport}: {m}")
