@@ -105,6 +105,32 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+_ext = None
+
+
+def load_ext():
+    """The thin torch extension over the same C ABI (csrc/torch_ext.cpp): returns ``torch.ops.siss_b200``. Built in
+    place on demand (g++ against the torch headers) and checked for staleness by content hash, like the library."""
+    global _ext
+    if _ext is not None:
+        return _ext
+    import torch
+    from . import build as _build
+    load()
+    if _build.ext_needs_build():
+        try:
+            _build.build_torch_ext()
+        except Exception as e:
+            raise SissLibraryError(f"{_build.EXT_PATH} is missing or stale and could not be built ({e}); set "
+                                   "SISS_BINDING=ctypes to use the ctypes binding of the same library") from e
+    try:
+        torch.ops.load_library(str(_build.EXT_PATH))
+    except OSError as e:  # pragma: no cover - depends on the environment
+        raise SissLibraryError(f"cannot load {_build.EXT_PATH}: {e}") from e
+    _ext = torch.ops.siss_b200
+    return _ext
+
+
 def error_string(code: int) -> str:
     return load().siss_error_string(code).decode()
 

@@ -7,6 +7,7 @@ current CUDA stream and never synchronise. CPU tensors are rejected: there is no
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -18,6 +19,28 @@ _DTYPES = {torch.float32: SISS_F32, torch.bfloat16: SISS_BF16, torch.float16: SI
 
 # incremented on every kernel launch made through this module (bench.py reports it)
 launch_count = 0
+
+# Two bindings of the SAME C ABI (include/siss_b200.h): "torch" = the thin torch extension csrc/torch_ext.cpp
+# (`torch.ops.siss_b200.*`: validation, output allocation and pointer marshalling in C++, one dispatcher call per op —
+# what BASELINE.json's north_star names), used for the ops on the per-step hot path; "ctypes" = the table in _lib.py,
+# the documented second binding and the only one for the cold ops. SISS_BINDING=ctypes forces it
+# everywhere (tests run both and compare bit for bit). Neither is a fallback for the other's failure.
+BINDING = os.environ.get("SISS_BINDING", "torch").lower()
+if BINDING not in ("torch", "ctypes"):
+    raise SissLibraryError(f"SISS_BINDING={BINDING!r}: expected 'torch' or 'ctypes'")
+
+
+def _ext_for(*tensors: torch.Tensor):
+    """torch.ops.siss_b200 after the cheap per-call checks the C++ side cannot turn into SissLibraryError."""
+    for t in tensors:
+        if not t.is_cuda:
+            raise SissLibraryError(
+                "siss_b200 ops need CUDA tensors on a B200; there is no CPU path (the CPU restatement is "
+                "oracle/, for tests only)")
+    idx = tensors[0].device.index
+    if idx not in _lib._devices_checked:
+        _need_cuda(*tensors)
+    return _lib.load_ext()
 
 
 def _count(n: int = 1) -> None:
@@ -119,6 +142,11 @@ def _norm_workspace(dev: torch.device) -> torch.Tensor:
 def add_noise(x0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
               alphas_cumprod: torch.Tensor) -> torch.Tensor:
     """x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) eps, rounding like diffusers' DDPMScheduler.add_noise."""
+    if BINDING == "torch":
+        out = _ext_for(x0, noise).add_noise(x0, noise, timesteps, alphas_cumprod)
+        if out.numel():
+            _count()
+        return out
     dev = _need_cuda(x0, noise, timesteps)
     if noise.shape != x0.shape or noise.dtype != x0.dtype:
         raise ValueError("noise must have the shape and dtype of the samples")
@@ -138,6 +166,11 @@ def add_noise(x0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
 def add_noise_pair(x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor,
                    alphas_cumprod: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Keep and forget batches noised with the shared eps and t in one pass (5 streams instead of 6)."""
+    if BINDING == "torch":
+        out = _ext_for(x0, a0, noise).add_noise_pair(x0, a0, noise, timesteps, alphas_cumprod)
+        if out[0].numel():
+            _count()
+        return out
     dev = _need_cuda(x0, a0, noise, timesteps)
     if not (x0.shape == a0.shape == noise.shape) or not (x0.dtype == a0.dtype == noise.dtype):
         raise ValueError("x0, a0 and noise must share shape and dtype")
@@ -176,6 +209,10 @@ def mixture_weights(xt_x: torch.Tensor, xt_a: torch.Tensor, x0: torch.Tensor, a0
                     sigma: torch.Tensor, lambd: float):
     """Row-select the mixture sample and compute (dist_x, dist_a, w_x, w_a). Returns
     (x_mix, dist_x, dist_a, w_x, w_a)."""
+    if BINDING == "torch":
+        out = _ext_for(xt_x, xt_a, x0, a0).mixture_weights(xt_x, xt_a, x0, a0, keep_mask, timesteps, gamma, sigma, float(lambd))
+        _count()
+        return out
     dev = _need_cuda(xt_x, xt_a, x0, a0, timesteps)
     if not (xt_x.shape == xt_a.shape == x0.shape == a0.shape):
         raise ValueError("noisy/original keep/forget batches must share one shape")
@@ -201,6 +238,11 @@ def add_noise_mixture(x0: torch.Tensor, a0: torch.Tensor, noise: torch.Tensor, k
                       timesteps: torch.Tensor, alphas_cumprod: torch.Tensor, gamma: torch.Tensor,
                       sigma: torch.Tensor, lambd: float):
     """Fused K1 o K2: returns (x_mix, dist_x, dist_a, w_x, w_a) straight from (x0, a0, eps)."""
+    if BINDING == "torch":
+        out = _ext_for(x0, a0, noise).add_noise_mixture(x0, a0, noise, keep_mask, timesteps, alphas_cumprod, gamma, sigma,
+                                                        float(lambd))
+        _count()
+        return out
     dev = _need_cuda(x0, a0, noise, timesteps)
     if not (x0.shape == a0.shape == noise.shape) or not (x0.dtype == a0.dtype == noise.dtype):
         raise ValueError("x0, a0 and noise must share shape and dtype")
@@ -267,6 +309,11 @@ def _k3_common(pred, x_mix, x0, a0, timesteps, gamma, sigma, w_x, w_a):
 
 def wmse_fwd_bwd(pred, x_mix, x0, a0, timesteps, gamma, sigma, w_x, w_a, go_x: float, go_a: float):
     """K3 fast path. Returns (grad_x, grad_a, row_loss_x, row_loss_a); grads in pred's dtype."""
+    if BINDING == "torch":
+        out = _ext_for(pred, x_mix, x0, a0, w_x, w_a).wmse_fwd_bwd(pred, x_mix, x0, a0, timesteps, gamma, sigma, w_x, w_a,
+                                                                   float(go_x), float(go_a))
+        _count()
+        return out
     dev, pred, x_mix, x0, a0, ts, g, s, w_x, w_a, B, D = _k3_common(pred, x_mix, x0, a0, timesteps, gamma, sigma,
                                                                      w_x, w_a)
     grad_x, grad_a = torch.empty_like(pred), torch.empty_like(pred)
@@ -365,6 +412,11 @@ def sqerr_bwd(pred, target, go_loss=None, go_scaled=None, alpha: float = 0.0):
 
 def dual_mse_fwd_bwd(pred_x, pred_a, target_x, target_a, go_x: float, go_a: float):
     """No-IS / EraseDiff fast path. Returns (grad_x, grad_a, row_loss_x, row_loss_a)."""
+    if BINDING == "torch":
+        out = _ext_for(pred_x, pred_a, target_x, target_a).dual_mse_fwd_bwd(pred_x, pred_a, target_x, target_a, float(go_x),
+                                                                            float(go_a))
+        _count()
+        return out
     dev = _need_cuda(pred_x, pred_a, target_x, target_a)
     if not (pred_x.shape == pred_a.shape == target_x.shape == target_a.shape):
         raise ValueError("preds and targets must share one shape")
@@ -413,6 +465,13 @@ def dual_mse_rng_fwd_bwd(pred_x, pred_a, target_x, go_x: float, go_a: float, see
 # ------------------------------------------------------------------------------------------------
 def norm3(g_x: torch.Tensor, g_a: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """{sum g_x^2, sum g_a^2, sum g_x g_a} as a float64[3] device tensor (K4a)."""
+    if BINDING == "torch":
+        ext = _ext_for(g_x, g_a)
+        if out is None:
+            out = torch.empty(3, dtype=torch.float64, device=g_x.device)
+        ext.norm3_(g_x, g_a, out)
+        _count()
+        return out
     dev = _need_cuda(g_x, g_a)
     if g_x.dtype != torch.float32 or g_a.dtype != torch.float32:
         raise SissLibraryError("gradient buffers must be float32")
@@ -431,6 +490,16 @@ def combine(g_x: torch.Tensor, g_a: torch.Tensor, sums3: torch.Tensor, mode: int
             stats: Optional[torch.Tensor] = None):
     """out = clip * (g_x - s g_a) (K4b). Returns (out, stats5) with stats5 = [||g_x||, ||g_a||, s,
     ||g_x - s g_a||, clip] on the device."""
+    if BINDING == "torch":
+        ext = _ext_for(g_x, g_a, sums3)
+        if out is None:
+            out = torch.empty_like(g_x)
+        if stats is None:
+            stats = torch.empty(5, dtype=torch.float32, device=g_x.device)
+        ext.combine_(g_x, g_a, sums3, int(mode), float(value), float(max_norm if max_norm is not None else 0.0),
+                     bool(inf_guard), out, stats)
+        _count()
+        return out, stats
     dev = _need_cuda(g_x, g_a, sums3)
     if g_x.dtype != torch.float32 or g_a.dtype != torch.float32 or sums3.dtype != torch.float64:
         raise SissLibraryError("gradient buffers must be float32 and sums3 float64")
@@ -456,6 +525,16 @@ def batch_stats(row_loss_x: Optional[torch.Tensor], row_loss_a: Optional[torch.T
                 w_a: Optional[torch.Tensor], elems_per_sample: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The 16 logging scalars of delete_celeb.py:626-656 in one launch (order: ``STAT_KEYS``).
     Inputs are the per-sample sums / weights K2 and K3 return; any may be None (-> NaN outputs)."""
+    if BINDING == "torch":
+        present = [t for t in (row_loss_x, row_loss_a, w_x, w_a) if t is not None]
+        if not present:
+            raise ValueError("batch_stats needs at least one input")
+        ext = _ext_for(*present)
+        if out is None:
+            out = torch.empty(16, dtype=torch.float32, device=present[0].device)
+        ext.batch_stats_(row_loss_x, row_loss_a, w_x, w_a, int(elems_per_sample), out)
+        _count()
+        return out
     present = [t for t in (row_loss_x, row_loss_a, w_x, w_a) if t is not None]
     if not present:
         raise ValueError("batch_stats needs at least one input")

@@ -53,7 +53,39 @@ def timeit(fn, n=200):
     return s.elapsed_time(e) / n * 1e3
 
 
+from siss_b200 import ops  # noqa: E402
+
 eager_us = timeit(one)
+ops.BINDING = "ctypes"
+eager_ctypes_us = timeit(one)
+ops.BINDING = "torch"
+
+
+# host cost of the binding alone: the four hot ops back to back on resident tensors, no UNet, no autograd
+def hot_ops():
+    x_mix, _, _, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, t, step.alphas_cumprod, step.gamma, step.sigma, 0.5)
+    ops.wmse_fwd_bwd(noise, x_mix, x0, a0, t, step.gamma, step.sigma, w_x, w_a, 1.0 / B, 1.0 / B)
+    ops.norm3(comb.g_x, comb.g_a, out=comb.sums3)
+    ops.combine(comb.g_x, comb.g_a, comb.sums3, 0, 5.0, 1.0, True, out=comb.g_x, stats=comb.stats)
+
+
+def host_us(fn, n=300):
+    import time
+    for _ in range(20):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    dt = time.perf_counter() - t0          # enqueue time only (the GPU work of these tiny shapes is shorter)
+    torch.cuda.synchronize()
+    return dt / n * 1e6
+
+
+hot_torch_us = host_us(hot_ops)
+ops.BINDING = "ctypes"
+hot_ctypes_us = host_us(hot_ops)
+ops.BINDING = "torch"
 side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
 with torch.cuda.stream(side):
     one()
@@ -63,4 +95,8 @@ with torch.cuda.graph(g):
     one()
 graph_us = timeit(g.replay)
 print(json.dumps({"shape": "delete_tshirt B=32 1x28x28 fp32, conv stand-in UNet", "eager_us_per_opt_step": eager_us,
-                  "cuda_graph_us_per_opt_step": graph_us, "speedup": eager_us / graph_us}))
+                  "eager_us_per_opt_step_ctypes_binding": eager_ctypes_us,
+                  "cuda_graph_us_per_opt_step": graph_us, "speedup": eager_us / graph_us,
+                  "eager_over_graph": eager_us / graph_us,
+                  "four_hot_ops_host_us": {"torch_extension": hot_torch_us, "ctypes": hot_ctypes_us},
+                  "note": "eager includes torch's own dispatch of the stand-in UNet forward and two backward passes"}))
