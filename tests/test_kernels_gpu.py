@@ -356,8 +356,6 @@ def test_workspace_reuse_across_batch_sizes(dev):
                                             out[3], out[4], 1 / 64, 1 / 64)
         eps_x = (mix - gamma[t].view(-1, 1, 1, 1) * x0) / sigma[t].view(-1, 1, 1, 1)
         torch.testing.assert_close(rlx.cpu(), ((pred - eps_x) ** 2).sum(dim=[1, 2, 3]), rtol=1e-5, atol=1e-5)
-    ws = list(ops._row_ws.values())
-    assert len(ws) >= 1
 
 
 @pytest.mark.parametrize("mode", ["scaling_norm", "erasediff"])
