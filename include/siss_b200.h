@@ -420,6 +420,26 @@ int siss_nvls_xcombine_bcast(float* mc_x, const float* shard_a, const double* sc
 int siss_scale_finalize(float* g, int64_t n, const double* scalar_slots1, const double* scalar_slots2, int world,
                         float scaling_norm, float max_norm, int inf_guard, float* stats5, siss_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The same exchange with the bytes moved by the COPY ENGINES (DMA over NVLink, ~700-730 GB/s per direction measured
+ * against 530-620 GB/s for SM-issued peer / multicast traffic) and the SMs working on local memory only. `staging` is a
+ * local buffer of 2 * (world-1) * shard_len floats. The shard is
+ * processed in `chunks` (1..16) pieces so that the kernels overlap the copies. Results are bit-identical to the
+ * siss_p2p_* pair (same rank-ordered sums). Side streams / events are owned by the library; all work is ordered against
+ * `stream`. Barriers between ranks exactly as for siss_p2p_*; h_* arrays as there (entry [rank] = the local buffer).
+ *
+ * siss_ce_reduce_norm3      DMA-pull this rank's shard of every peer's G_a (and G_x, x_mode 0) + rank-ordered sum + K4a.
+ * siss_ce_combine_allgather K4b on the shard into the own buffer + DMA-push to every peer.
+ * (x_mode 2 of the reduce serves as phase 1 of the pipelined schedule above, followed by siss_nvls_xcombine_bcast.)
+ * ---------------------------------------------------------------------------------------- */
+int siss_ce_reduce_norm3(const float* const* h_peers_x, const float* const* h_peers_a, double* const* h_peer_scalars,
+                         int world, int rank, int64_t shard_len, float* staging, float* shard_x, float* shard_a,
+                         double* sums3_local, int x_mode, int chunks, void* workspace, siss_stream_t stream);
+
+int siss_ce_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
+                              float* const* h_peers_out, int world, int rank, int64_t shard_len, int chunks,
+                              int mode, float value, float max_norm, int inf_guard, float* stats5, siss_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

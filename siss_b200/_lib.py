@@ -66,6 +66,8 @@ SIGNATURES = {
                                        _P, _D, _P, _P]),
     "siss_nvls_xcombine_bcast": (_I, [_P, _P, _P, _P, _I, _I, _L, _F, _I, _P, _P]),
     "siss_scale_finalize": (_I, [_P, _L, _P, _P, _I, _F, _F, _I, _P, _P]),
+    "siss_ce_reduce_norm3": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "siss_ce_combine_allgather": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _I, _F, _F, _I, _P, _P]),
 }
 
 _lib = None

@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libsiss_b200.so"
 HASH_PATH = PKG_DIR / "libsiss_b200.so.srchash"
-SOURCES = ["rowwise.cu", "wmse.cu", "combine.cu", "p2p.cu", "nvls.cu", "stats.cu", "optim.cu", "multitensor.cu", "membership.cu", "rng.cu"]
+SOURCES = ["rowwise.cu", "wmse.cu", "combine.cu", "p2p.cu", "nvls.cu", "ce.cu", "stats.cu", "optim.cu", "multitensor.cu", "membership.cu", "rng.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -94,4 +94,44 @@ __device__ __forceinline__ void publish_rank_sums(double (&acc)[3], double* red 
     }
 }
 
+// Chunked variant for the copy-engine schedules (ce.cu), where one logical reduce is a SEQUENCE of launches on one
+// stream (chunk c is reduced while chunk c+1 is still being copied): the last CTA of each launch adds the launch's
+// total to the running totals `run3` (device memory; overwritten by the first chunk) in launch order — still a fixed
+// summation order — and only the last chunk's launch publishes.
+__device__ __forceinline__ void publish_rank_sums_chunked(double (&acc)[3], double* red, int* flag, const P2PWorkspace& ws,
+                                                          double* run3, int first, int last, double* sums3_local,
+                                                          const PeerOut& pub, int world, int rank) {
+    block_sum<3>(acc, red);
+    if (threadIdx.x == 0) {
+        ws.partials[3 * blockIdx.x + 0] = acc[0];
+        ws.partials[3 * blockIdx.x + 1] = acc[1];
+        ws.partials[3 * blockIdx.x + 2] = acc[2];
+    }
+    if (last_cta_ticket(ws.counter, gridDim.x, flag)) {
+        if (threadIdx.x < 32) {
+            double t[3] = {0.0, 0.0, 0.0};
+            const volatile double* p = ws.partials;
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) {
+                t[0] += p[3 * b + 0]; t[1] += p[3 * b + 1]; t[2] += p[3 * b + 2];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] = warp_sum(t[k]);
+            if (!first) {
+                const volatile double* r = run3;
+                t[0] += r[0]; t[1] += r[1]; t[2] += r[2];
+            }
+            __syncwarp();
+            if (threadIdx.x == 0) {
+                run3[0] = t[0]; run3[1] = t[1]; run3[2] = t[2];
+                if (last && sums3_local) { sums3_local[0] = t[0]; sums3_local[1] = t[1]; sums3_local[2] = t[2]; }
+            }
+            if (last && (int)threadIdx.x < world) {
+                double* dst = pub.scalars[threadIdx.x] + 4 * rank;
+                dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2]; dst[3] = 0.0;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
 }  // namespace siss

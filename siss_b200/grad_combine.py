@@ -39,12 +39,14 @@ class GradCombiner:
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group: Optional[dist.ProcessGroup] = None,
                  distributed: Optional[bool] = None, transport: str = "auto"):
         """``transport`` selects how the data-parallel exchange is carried when world > 1:
-        ``"p2p"``  fused peer-memory kernels over NVLink (siss_b200/p2p.py, csrc/p2p.cu);
-        ``"nccl"`` torch.distributed collectives around K4a/K4b;
-        ``"auto"`` p2p on CUDA with 2 or 4 ranks when symmetric memory can be set up, else nccl. (Measured
-        on 8xB200: the fused kernels beat NCCL by ~30 % at N=2 — 1.28 vs 1.81 ms for P = 114 M — and tie at
-        N=4; at N=8 NCCL's in-switch (NVLS) reduce-scatter is ~6 % ahead, 2.1 vs 2.26 ms. Both sit at the
-        ~520-570 GB/s per-direction ceiling of bidirectional all-to-all NVLink traffic.)"""
+        ``"p2p"`` fused peer-memory kernels over NVLink (csrc/p2p.cu); ``"nvls"`` the same through the NVSwitch's
+        in-fabric reduction / replication (multimem, csrc/nvls.cu); ``"ce"`` bytes moved by the copy engines, SMs on
+        local memory only (csrc/ce.cu); ``"pipe"`` / ``"pipe_nvls"`` / ``"pipe_ce"`` the pipelined schedule (G_a first,
+        then reduce + combine + broadcast of G_x in one multicast kernel, clip afterwards; scaling-norm modes);
+        ``"nccl"`` torch.distributed collectives around K4a/K4b (one grouped reduce-scatter);
+        ``"auto"`` every schedule the node supports AND the NCCL collectives are timed on the real buffers at
+        construction (max over ranks, so the choice is collective) and the fastest is kept — separately for the
+        full exchange and for the exchange whose G_x shard was reduced early (siss_b200/p2p.py::PeerExchange.tune)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradCombiner needs at least one parameter that requires grad")
@@ -72,7 +74,7 @@ class GradCombiner:
         self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's shard is 16B aligned
         self.peer = None
         self.tuning = {}
-        peer_names = ("p2p", "nvls", "pipe", "pipe_nvls")
+        peer_names = ("p2p", "nvls", "ce", "pipe", "pipe_nvls", "pipe_ce")
         if transport not in ("auto", "nccl") + peer_names:
             raise ValueError(f"unknown transport {transport!r}")
         want_peer = transport != "nccl"
@@ -101,7 +103,8 @@ class GradCombiner:
                 if transport not in self.peer.available():
                     raise RuntimeError(f"transport {transport!r} needs NVSwitch multicast, which this node does not provide")
                 self.peer.algo = transport
-                three = transport if transport in ("p2p", "nvls") else ("nvls" if transport == "pipe_nvls" else "p2p")
+                three = transport if transport in ("p2p", "nvls", "ce") else \
+                    {"pipe": "p2p", "pipe_nvls": "nvls", "pipe_ce": "ce"}[transport]
                 self.peer.algo3 = self.peer.algo_xpre = three
         elif self.world > 1 and transport in peer_names:
             raise RuntimeError(f"transport {transport!r} needs CUDA and 2, 4 or 8 ranks on one node")
@@ -271,11 +274,11 @@ class GradCombiner:
         name = "nccl" if (self._nccl_xpre if x_prereduced else self._nccl_full) else \
             (self.peer.algo_xpre if x_prereduced else self.peer.algo)
         nx = 0 if x_prereduced else 1
-        if name in ("p2p", "nccl"):          # NCCL: ring-equivalent count (its NVLS path is internal to the library)
+        if name in ("p2p", "ce", "nccl"):    # NCCL: ring-equivalent count (its NVLS path is internal to the library)
             out = inb = (N - 1) * S4 * (1 + nx) + (N - 1) * S4
         elif name == "nvls":
             out, inb = P4 * (1 + nx) + S4, S4 * (1 + nx) + P4
-        elif name == "pipe":
+        elif name in ("pipe", "pipe_ce"):
             out, inb = (N - 1) * S4 + P4 + S4, (N - 1) * S4 + S4 + P4
         else:                                # pipe_nvls
             out, inb = P4 + P4 + S4, S4 + S4 + P4

@@ -3,7 +3,7 @@
 ``G_x`` and ``G_a`` live in symmetric memory (``torch.distributed._symmetric_memory``: every rank's
 allocation is mapped into every process of the node, and — on an NVSwitch box — bound to one multicast
 address), and the exchange + K4 run as fused kernels of libsiss_b200.so (csrc/p2p.cu, csrc/nvls.cu)
-instead of five NCCL collectives around two kernels. Four schedules (``algo``):
+instead of five NCCL collectives around two kernels. Schedules (``algo``):
 
   "p2p"        barrier | siss_p2p_reduce_norm3 (reduce-scatter x2 + K4a, peer loads)   | barrier
                        | siss_p2p_combine_allgather (K4b + all-gather, peer stores)    | barrier
@@ -14,6 +14,11 @@ instead of five NCCL collectives around two kernels. Four schedules (``algo``):
                (reduce traffic outbound and gather traffic inbound at the same time) | barrier |
                local clip pass
   "pipe_nvls"  as "pipe" with the G_a reduce through the switch as well
+  "ce"         the three stages with the bytes moved by the COPY ENGINES (csrc/ce.cu): DMA pulls of the peers' shards
+               into staging, chunked so that the rank-ordered sum / K4a of piece c overlaps the copy of piece c+1;
+               K4b per piece into the own buffer + DMA pushes. DMA reaches 700-730 GB/s per direction where SM-issued
+               peer or multicast traffic reaches 530-620 (profiles/r2_ce_probe_w2.json). Bit-identical to "p2p".
+  "pipe_ce"    as "pipe" with the G_a reduce by DMA
 
 Which one is fastest depends on the rank count (the in-switch forms move more bytes at N = 2 and fewer
 at N = 8), so :meth:`PeerExchange.tune` measures them on the real buffers at start-up and the choice is
@@ -23,6 +28,7 @@ multicast binding and the stream-ordered barriers.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Callable, Dict, Optional, Sequence
 
 import torch
@@ -31,9 +37,11 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import SISS_COMBINE_SCALING_NORM
 
-THREE_STAGE = ("p2p", "nvls")
-PIPELINED = ("pipe", "pipe_nvls")
+THREE_STAGE = ("p2p", "nvls", "ce")
+PIPELINED = ("pipe", "pipe_nvls", "pipe_ce")
 ALGOS = THREE_STAGE + PIPELINED
+NEEDS_MULTICAST = ("nvls",) + PIPELINED
+CE_CHUNKS = max(1, min(16, int(os.environ.get("SISS_CE_CHUNKS", "4"))))
 
 
 class PeerExchange:
@@ -75,6 +83,7 @@ class PeerExchange:
         self.shard_a = torch.empty(self.shard_len, dtype=f32, device=device)
         self.sums_local = torch.zeros(3, dtype=f64, device=device)
         self.ws = torch.zeros(_lib.load().siss_p2p_workspace_bytes(), dtype=torch.uint8, device=device)
+        self._staging = None       # DMA landing area of the copy-engine schedules (allocated on first use)
         self.algo = "p2p"          # schedule used when combine() is not told otherwise (see tune())
         self.algo_xpre = "p2p"     # ... when G_x arrives already reduced (three-stage schedules only)
         self.algo3 = "p2p"         # ... best three-stage schedule of the full exchange (EraseDiff cannot be pipelined)
@@ -84,7 +93,13 @@ class PeerExchange:
 
     # ------------------------------------------------------------------------------------------
     def available(self) -> Sequence[str]:
-        return ALGOS if self.has_multicast else ("p2p",)
+        return ALGOS if self.has_multicast else tuple(a for a in ALGOS if a not in NEEDS_MULTICAST)
+
+    @property
+    def staging(self) -> torch.Tensor:
+        if self._staging is None:
+            self._staging = torch.empty(2 * (self.world - 1) * self.shard_len, dtype=torch.float32, device=self.g_x.device)
+        return self._staging
 
     def _resolve(self, algo: Optional[str], mode: int, x_prereduced: bool) -> str:
         if x_prereduced:
@@ -96,7 +111,7 @@ class PeerExchange:
             algo = self.algo_xpre if x_prereduced else self.algo3
         if algo not in ALGOS:
             raise ValueError(f"unknown exchange schedule {algo!r}")
-        if algo != "p2p" and not self.has_multicast:
+        if algo in NEEDS_MULTICAST and not self.has_multicast:
             raise RuntimeError(f"schedule {algo!r} needs a multicast (NVLS) binding, which this node does not provide")
         return algo
 
@@ -117,7 +132,12 @@ class PeerExchange:
     # ------------------------------------------------------------------------------------------
     def _reduce(self, lib, stream, algo: str, x_mode: int) -> None:
         P = ctypes.c_void_p
-        if algo == "nvls":
+        if algo == "ce":
+            _lib.check(lib.siss_ce_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
+                                                self.shard_len, self.staging.data_ptr(), self.shard_x.data_ptr(),
+                                                self.shard_a.data_ptr(), self.sums_local.data_ptr(), x_mode, CE_CHUNKS,
+                                                self.ws.data_ptr(), stream), "siss_ce_reduce_norm3")
+        elif algo == "nvls":
             _lib.check(lib.siss_nvls_reduce_norm3(P(self.mc_x), P(self.mc_a), self.ptrs_s, self.world, self.rank,
                                                   self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
                                                   self.sums_local.data_ptr(), x_mode, self.ws.data_ptr(), stream),
@@ -143,6 +163,7 @@ class PeerExchange:
         algo = algo if algo in THREE_STAGE else (self.algo_xpre if x_prereduced else self.algo3)
         if algo == "nvls" and not (self.has_multicast and self.mc_p):
             algo = "p2p"
+        # "ce": DMA reduce, then the peer-store kernel for the fused update + parameter all-gather
         self.h_x.barrier(channel=0)
         self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
         self.h_x.barrier(channel=1)
@@ -174,7 +195,7 @@ class PeerExchange:
         mn, ig = float(max_norm), int(bool(inf_guard))
         self.h_x.barrier(channel=0)        # every rank's G_x / G_a are complete
         if algo in PIPELINED:
-            self._reduce(lib, stream, "nvls" if algo == "pipe_nvls" else "p2p", 2)          # phase 1: G_a, sum a^2
+            self._reduce(lib, stream, {"pipe": "p2p", "pipe_nvls": "nvls", "pipe_ce": "ce"}[algo], 2)   # phase 1: G_a, sum a^2
             self.h_x.barrier(channel=1)    # every rank's sum a^2 is in every slot array
             _lib.check(lib.siss_nvls_xcombine_bcast(P(self.mc_x), self.shard_a.data_ptr(), self.slots1.data_ptr(),
                                                     self.ptrs_s2, self.world, self.rank, self.shard_len, float(value),
@@ -187,7 +208,13 @@ class PeerExchange:
             return
         self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
         self.h_x.barrier(channel=1)        # every rank's scalar slot has been written everywhere
-        if algo == "nvls":
+        if algo == "ce":
+            _lib.check(lib.siss_ce_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
+                                                     self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
+                                                     self.shard_len, CE_CHUNKS, int(mode), float(value), mn, ig,
+                                                     stats.data_ptr(), stream), "siss_ce_combine_allgather")
+            ops._count(CE_CHUNKS - 1)      # one kernel per piece on both sides
+        elif algo == "nvls":
             _lib.check(lib.siss_nvls_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
                                                        self.scalars.data_ptr(), P(self.mc_x), self.world, self.rank,
                                                        self.shard_len, int(mode), float(value), mn, ig,

@@ -107,7 +107,7 @@ def _worker(rank, world, port, q):
     probe = GradCombiner(TinyNet().to(torch.device("cuda", rank)).parameters(), transport="p2p")
     multicast = probe.peer.has_multicast            # NVSwitch multicast bound: the in-switch schedules exist too
     del probe
-    for transport in ("nccl", "p2p", "auto") + (("nvls", "pipe", "pipe_nvls") if multicast else ()):
+    for transport in ("nccl", "p2p", "ce", "auto") + (("nvls", "pipe", "pipe_nvls", "pipe_ce") if multicast else ()):
         out[transport] = _run(rank, world, 8, 2, transport)
         out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
         if transport in ("nccl", "p2p"):

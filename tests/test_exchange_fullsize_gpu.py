@@ -3,7 +3,7 @@ kernels, NVSwitch multicast kernels (three-stage and pipelined), NCCL collective
 1-rank evaluation  sum_r G^(r)  ->  siss_norm3  ->  siss_combine  of the same per-rank random gradients.
 
 What must hold:
-  * "p2p" (peer loads, fixed rank-order sums): output BIT-IDENTICAL to clip * (X - s A) of the rank-ordered sums, for
+  * "p2p" and "ce" (peer loads / DMA pulls, fixed rank-order sums): output BIT-IDENTICAL to clip * (X - s A) of the rank-ordered sums, for
     the full exchange and with the G_x shard reduced beforehand (x_prereduced), SISS and EraseDiff scalars;
   * multicast / NCCL schedules (the fabric or NCCL chooses the order of the N fp32 additions): element-wise within
     2e-6 of the largest gradient entry, scalars (norms, s, total norm, clip) rtol 2e-6;
@@ -105,7 +105,7 @@ def _worker(rank, world, port, q, P):
                     pe.combine(mode, value, 1.0, False, probe.stats, x_prereduced=xpre, algo=algo)
                     used = pe._resolve(algo, mode, xpre)
                     name = f"{algo}/{case}/{'xpre' if xpre else 'full'}(ran {used})"
-                    report[name] = _check(name, pe.g_x[:P], probe.stats, X, A, ref_out, ref_stats, used == "p2p", rank,
+                    report[name] = _check(name, pe.g_x[:P], probe.stats, X, A, ref_out, ref_stats, used in ("p2p", "ce"), rank,
                                           world, errs)
         del probe
         torch.cuda.empty_cache()

@@ -90,6 +90,13 @@ def main():
                     P(pe.mc_x), pe.shard_a.data_ptr(), pe.slots1.data_ptr(), pe.ptrs_s2, N, rank, comb.shard_len, 500.0, 0,
                     pe.ws.data_ptr(), stream), "xcombine"), P4 + S4, S4 + P4),
             })
+        from siss_b200.p2p import CE_CHUNKS
+        phases.update({
+            "ce_reduce_x_a": (lambda: pe._reduce(lib, stream, "ce", 0), (N - 1) * S4 * 2, (N - 1) * S4 * 2),
+            "ce_reduce_a": (lambda: pe._reduce(lib, stream, "ce", 2), (N - 1) * S4, (N - 1) * S4),
+            "ce_combine_allgather": (lambda: _lib.check(lib.siss_ce_combine_allgather(
+                pe.shard_x.data_ptr(), pe.shard_a.data_ptr(), pe.scalars.data_ptr(), pe.ptrs_x, N, rank, comb.shard_len,
+                CE_CHUNKS, SN, 500.0, 1.0, 0, stats.data_ptr(), stream), "gather"), (N - 1) * S4, (N - 1) * S4)})
         phases["scale_finalize(local, 8 B/param HBM)"] = (lambda: _lib.check(lib.siss_scale_finalize(
             pe.g_x.data_ptr(), comb.total, pe.slots1.data_ptr(), pe.slots2.data_ptr(), N, 500.0, 1.0, 0, stats.data_ptr(),
             stream), "scale"), 0, 0)
@@ -106,7 +113,7 @@ def main():
         sched = {}
         for a in pe.available():
             sched[a] = timeit(lambda a=a: pe.combine(SN, 500.0, 1.0, False, stats, algo=a)) - t_bar
-            if a in ("p2p", "nvls"):
+            if a in ("p2p", "nvls", "ce"):
                 sched[a + "+xpre"] = timeit(lambda a=a: pe.combine(SN, 500.0, 1.0, False, stats, x_prereduced=True, algo=a)) - t_bar
         sched["nccl"] = timeit(lambda: comb._nccl_exchange(SN, 500.0, 1.0, False, False)) - t_bar
         sched["nccl+xpre"] = timeit(lambda: comb._nccl_exchange(SN, 500.0, 1.0, False, True)) - t_bar
