@@ -32,9 +32,11 @@ constexpr int kMaxChunks = 16;
 struct CeCtx {
     bool ready = false;
     cudaStream_t side[kMaxWorld];                // pulls from peer p
+    cudaStream_t side2[kMaxWorld];               // second buffer's pulls from peer p (two DMA engines per peer)
     cudaStream_t push[kMaxWorld];                // pushes to peer p (separate: a push must not queue behind later pulls)
     cudaEvent_t fork;
-    cudaEvent_t landed[kMaxWorld][kMaxChunks];   // piece c of peer p's data has arrived / has been sent
+    cudaEvent_t landed[kMaxWorld][kMaxChunks];   // piece c of peer p's data has arrived
+    cudaEvent_t landed2[kMaxWorld][kMaxChunks];  // ... of the second buffer
     cudaEvent_t made[kMaxChunks];                // kernel of piece c has finished (gather side)
     cudaEvent_t joined[kMaxWorld];
 };
@@ -47,9 +49,13 @@ static int ce_ctx(CeCtx** out) {
         for (int p = 0; p < kMaxWorld; ++p) {
             if ((e = cudaStreamCreateWithFlags(&c.side[p], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
             if ((e = cudaStreamCreateWithFlags(&c.push[p], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+            if ((e = cudaStreamCreateWithFlags(&c.side2[p], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
             if ((e = cudaEventCreateWithFlags(&c.joined[p], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
             for (int k = 0; k < kMaxChunks; ++k)
+            {
                 if ((e = cudaEventCreateWithFlags(&c.landed[p][k], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+                if ((e = cudaEventCreateWithFlags(&c.landed2[p][k], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            }
         }
         for (int k = 0; k < kMaxChunks; ++k)
             if ((e = cudaEventCreateWithFlags(&c.made[k], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
@@ -168,9 +174,16 @@ ce_combine_chunk_kernel(const float* __restrict__ shard_x, const float* __restri
     }
 }
 
-static inline void piece(long long nvec, int chunks, int c, long long& lo, long long& hi) {
-    lo = nvec * c / chunks;
-    hi = nvec * (c + 1) / chunks;
+// Piece c of `chunks` with linearly graded sizes: `descending` (reduce side: chunks, chunks-1, ..., 1 parts) makes the
+// LAST piece — whose kernel cannot overlap any copy — the smallest; ascending (gather side) makes the FIRST piece —
+// whose kernel must finish before any push can start — the smallest.
+static inline void piece(long long nvec, int chunks, int c, bool descending, long long& lo, long long& hi) {
+    const long long total = (long long)chunks * (chunks + 1) / 2;
+    auto prefix = [&](int k) -> long long {     // parts in pieces [0, k)
+        return descending ? (long long)k * chunks - (long long)k * (k - 1) / 2 : (long long)k * (k + 1) / 2;
+    };
+    lo = nvec * prefix(c) / total;
+    hi = nvec * prefix(c + 1) / total;
 }
 
 // DMA-pull pieces of this rank's shard from every peer into staging, one side stream per peer; `nbuf` buffers per piece.
@@ -183,27 +196,30 @@ static int ce_pull(CeCtx* cx, cudaStream_t st, int world, int rank, long long nv
         const int p = (rank + k) % world;             // rotated: at any moment every rank pulls from a different peer
         const int j = p < rank ? p : p - 1;           // slot of peer p in the staging arrays
         if ((e = cudaStreamWaitEvent(cx->side[p], cx->fork, 0)) != cudaSuccess) return (int)e;
+        if (srcs1 && (e = cudaStreamWaitEvent(cx->side2[p], cx->fork, 0)) != cudaSuccess) return (int)e;
         for (int c = 0; c < chunks; ++c) {
             long long lo, hi;
-            piece(nvec, chunks, c, lo, hi);
+            piece(nvec, chunks, c, true, lo, hi);
             const size_t bytes = (size_t)(hi - lo) * 16;
-            if (bytes) {
-                if (srcs0 && (e = cudaMemcpyAsync(staging0 + (long long)j * shard_len + 4 * lo, srcs0[p] + base_elem + 4 * lo,
-                                                  bytes, cudaMemcpyDeviceToDevice, cx->side[p])) != cudaSuccess) return (int)e;
-                if (srcs1 && (e = cudaMemcpyAsync(staging1 + (long long)j * shard_len + 4 * lo, srcs1[p] + base_elem + 4 * lo,
-                                                  bytes, cudaMemcpyDeviceToDevice, cx->side[p])) != cudaSuccess) return (int)e;
-            }
+            if (bytes && (e = cudaMemcpyAsync(staging0 + (long long)j * shard_len + 4 * lo, srcs0[p] + base_elem + 4 * lo,
+                                              bytes, cudaMemcpyDeviceToDevice, cx->side[p])) != cudaSuccess) return (int)e;
             if ((e = cudaEventRecord(cx->landed[p][c], cx->side[p])) != cudaSuccess) return (int)e;
+            if (srcs1) {
+                if (bytes && (e = cudaMemcpyAsync(staging1 + (long long)j * shard_len + 4 * lo, srcs1[p] + base_elem + 4 * lo,
+                                                  bytes, cudaMemcpyDeviceToDevice, cx->side2[p])) != cudaSuccess) return (int)e;
+                if ((e = cudaEventRecord(cx->landed2[p][c], cx->side2[p])) != cudaSuccess) return (int)e;
+            }
         }
     }
     return 0;
 }
 
-static int ce_wait_piece(CeCtx* cx, cudaStream_t st, int world, int rank, int c) {
+static int ce_wait_piece(CeCtx* cx, cudaStream_t st, int world, int rank, int c, bool two) {
     for (int p = 0; p < world; ++p) {
         if (p == rank) continue;
         cudaError_t e = cudaStreamWaitEvent(st, cx->landed[p][c], 0);
         if (e != cudaSuccess) return (int)e;
+        if (two && (e = cudaStreamWaitEvent(st, cx->landed2[p][c], 0)) != cudaSuccess) return (int)e;
     }
     return 0;
 }
@@ -214,7 +230,7 @@ static int ce_push_piece(CeCtx* cx, cudaStream_t st, int world, int rank, long l
     cudaError_t e;
     if ((e = cudaEventRecord(cx->made[c], st)) != cudaSuccess) return (int)e;
     long long lo, hi;
-    piece(nvec, chunks, c, lo, hi);
+    piece(nvec, chunks, c, false, lo, hi);
     const size_t bytes = (size_t)(hi - lo) * 16;
     for (int k = 1; k < world; ++k) {
         const int p = (rank + k) % world;
@@ -275,9 +291,9 @@ int siss_ce_reduce_norm3(const float* const* h_peers_x, const float* const* h_pe
     P2PWorkspace ws = carve_p2p(workspace);
     double* run3 = ce_run3(workspace);
     for (int c = 0; c < chunks; ++c) {
-        if ((rc = ce_wait_piece(cx, st, world, rank, c))) return rc;
+        if ((rc = ce_wait_piece(cx, st, world, rank, c, x_mode == 0))) return rc;
         long long lo, hi;
-        piece(nvec, chunks, c, lo, hi);
+        piece(nvec, chunks, c, true, lo, hi);
         const int first = c == 0, last = c == chunks - 1;
 #define SISS_CE_REDUCE(WORLD_, U_)                                                                                      \
         do {                                                                                                           \
@@ -313,7 +329,7 @@ int siss_ce_combine_allgather(const float* shard_x, const float* shard_a, const 
     float* out_local = h_peers_out[rank] + base;
     for (int c = 0; c < chunks; ++c) {
         long long lo, hi;
-        piece(nvec, chunks, c, lo, hi);
+        piece(nvec, chunks, c, false, lo, hi);
         const int grid = p2p_grid(hi - lo, 4);
         switch (world) {
             case 2: ce_combine_chunk_kernel<2, 4><<<grid, kThreads, 0, st>>>(shard_x, shard_a, scalar_slots, lo, hi, out_local, mode, value, max_norm, inf_guard, stats5, c == 0); break;
