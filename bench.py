@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--no-copy-floor", action="store_true", help="skip the same-bytes D2D copy floor (keeps ncu launch lists clean)")
     ap.add_argument("--cpu-steps", type=int, default=16)
-    ap.add_argument("--transport", choices=["auto", "p2p", "nccl"], default="auto",
+    ap.add_argument("--transport", choices=["auto", "p2p", "nvls", "ce", "pipe", "pipe_nvls", "pipe_ce", "nccl"], default="auto",
                     help="N>1 gradient exchange: fused NVLink peer-memory kernels or NCCL collectives")
     return ap.parse_args()
 
@@ -86,8 +86,11 @@ class BenchUNet(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.tensor(0.05))
         self.bank = torch.nn.Parameter(torch.zeros(max(n_params - 2, 1)))
 
-    def forward(self, x, timesteps, return_dict=False, **kw):
-        return (x.float() * self.scale + (self.bias + self.bank.sum() * 1e-6),)
+    def forward(self, x, timesteps, encoder_hidden_states=None, return_dict=False, **kw):
+        out = x.float() * self.scale + (self.bias + self.bank.sum() * 1e-6)
+        if encoder_hidden_states is not None:          # delete_sd: text conditioning [B, 77, 768] is consumed
+            out = out + encoder_hidden_states.float().mean() * 0.01
+        return (out,)
 
 
 class StandInUNet(torch.nn.Module):
@@ -192,6 +195,8 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thr = None
         try:
+            if device_index < 0:
+                raise RuntimeError("clock sampling disabled (SISS_BENCH_NO_NVML=1)")
             import pynvml
             pynvml.nvmlInit()
             uuid = str(torch.cuda.get_device_properties(device_index).uuid)
@@ -219,7 +224,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -242,31 +247,45 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle's restatement of the reference loop on host cores
 # --------------------------------------------------------------------------------------------------
-def make_cpu_step(args):
+def celeb_workload(args):
+    return dict(name="delete_celeb", B=args.batch, chw=(args.channels, args.res, args.res), dt=torch_dtype(args.dtype),
+                P=args.params, lambd=0.5, scaling_norm=500.0, t_range=(999, 1000), sd=False, cond=None, inf_guard=False)
+
+
+# BASELINE.json configs[0] and configs[3]: parity-test cases that also get an e2e and a CPU number
+TSHIRT = dict(name="delete_tshirt", B=32, chw=(1, 28, 28), dt=torch.float32, P=15_000_000, lambd=0.5, scaling_norm=5.0,
+              t_range=(0, 1000), sd=False, cond=None, inf_guard=True)
+SD = dict(name="delete_sd", B=1, chw=(4, 64, 64), dt=torch.float32, P=859_520_964, lambd=0.5, scaling_norm=750.0,
+          t_range=(999, 1000), sd=True, cond=(77, 768), inf_guard=False)
+
+
+def make_cpu_step(w):
+    """One optimiser step of the reference's CPU path for workload ``w`` (oracle port of the loop, torch CPU)."""
     from oracle import siss_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    dt = torch_dtype(args.dtype)
-    B = args.batch
-    shape = (B, args.channels, args.res, args.res)
+    dt, B = w["dt"], w["B"]
+    shape = (B,) + tuple(w["chw"])
     x0, a0 = synth_images(shape, dt, seed=42)
-    ac = O.make_alphas_cumprod()
+    ac = O.make_alphas_cumprod(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear") if w["sd"] else O.make_alphas_cumprod()
     gamma, sigma = O.gamma_sigma(ac)
     loss = O.OracleDeletionLoss(gamma, sigma)
-    unet = BenchUNet(args.params)
+    unet = BenchUNet(w["P"])
     loop = O.ReferenceGradLoop(unet, train_batch_size=B, grad_accum_steps=1)
+    cond = {"encoder_hidden_states": torch.randn(B, *w["cond"])} if w["cond"] else {}
+    lo, hi = w["t_range"]
     torch.manual_seed(42)
 
     def step():
-        # delete_celeb.py:581-603: shared noise, t == 999, two add_noise calls
+        # delete_celeb.py:581-603: shared noise, timesteps, two add_noise calls
         noise = torch.randn(shape, dtype=dt)
-        t = torch.randint(999, 1000, (B,)).long()
+        t = torch.randint(lo, hi, (B,)).long()
         all_d = {"og_latents": x0, "noisy_latents": O.add_noise(ac, x0, noise, t)}
         del_d = {"og_latents": a0, "noisy_latents": O.add_noise(ac, a0, noise, t)}
-        items = loss.importance_sampling_with_mixture(unet, t, noise, {}, all_d, del_d, lambd=0.5)   # :622
+        items = loss.importance_sampling_with_mixture(unet, t, noise, cond, all_d, del_d, lambd=w["lambd"])   # :622
         stats = O.batch_stats(items)                                                                 # :626-656
         loop.micro_step(items, retain_graph=True)                                                    # :686-711
-        out = loop.sync_step(False, scaling_norm=500.0, max_norm=1.0)                                # :714-767
+        out = loop.sync_step(False, scaling_norm=w["scaling_norm"], max_norm=1.0, inf_guard=w["inf_guard"])   # :714-767
         stats["gradient/norm_loss_a"] = float(out["norm_a"])
         for p in unet.parameters():                                                                  # zero_grad()
             p.grad = None
@@ -275,8 +294,8 @@ def make_cpu_step(args):
     return step, threads
 
 
-def time_cpu(args, steps, warmup):
-    step, threads = make_cpu_step(args)
+def time_cpu(w, steps, warmup):
+    step, threads = make_cpu_step(w)
     for _ in range(warmup):
         step()
     times = []
@@ -291,7 +310,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU reference arm
-    times, threads = time_cpu(args, args.steps, args.warmup)
+    times, threads = time_cpu(celeb_workload(args), args.steps, args.warmup)
     total = sum(times)
     value = args.batch * len(times) / total
     sample = (f"full workload per step: B={args.batch} x {args.channels}x{args.res}x{args.res} {args.dtype}, "
@@ -517,6 +536,182 @@ def extra_configs(dev):
     return out
 
 
+def measure_e2e(w, dev, n, rank, steps, warmup, transport, barrier, dist):
+    """End-to-end numbers of workload ``w`` through the public API, host buffers in, statistics out, every step:
+
+        DeviceFeeder (pinned H2D, double-buffered, copy stream)  ->  UnlearnStep.micro_step  ->  batch_stats
+        ->  UnlearnStep.sync_step (GradCombiner)  ->  D2H of 21 scalars + event sync
+
+    with a P-parameter stub UNet whose forward / backward are a few streaming passes. Three variants of the same loop:
+      eager        eps / t drawn with torch as the reference does (delete_celeb.py:581-598), CPU Bernoulli mask
+      device_rng   opt-in counter-based device RNG: eps generated inside K1oK2, t and the mask drawn on the device
+      graph        device_rng variant captured as ONE CUDA graph per feeder slot and replayed (N = 1 only)
+    plus a stage-by-stage breakdown of the eager loop from CUDA events (UnlearnStep.stage_hook)."""
+    from siss_b200.feed import DeviceFeeder
+    from siss_b200.grad_combine import GradCombiner
+    from siss_b200.rng import DeviceRng
+    from siss_b200.scheduler import SissDDPMScheduler
+    from siss_b200.step import UnlearnStep, batch_stats
+    B, dt, P = w["B"], w["dt"], w["P"]
+    shape = (B,) + tuple(w["chw"])
+    D = shape[1] * shape[2] * shape[3]
+    sched = SissDDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear") if w["sd"] \
+        else SissDDPMScheduler()
+    unet = BenchUNet(P).to(dev)
+    comb = GradCombiner(unet.parameters(), transport=transport)
+    common = dict(loss_fn="importance_sampling_with_mixture", train_batch_size=B * n, lambd=w["lambd"],
+                  scaling_norm=w["scaling_norm"], max_norm=1.0, inf_guard=w["inf_guard"])
+    step = UnlearnStep(unet, sched, comb, **common)
+    x0_h, a0_h = synth_images(shape, dt, seed=42 + rank)
+    hosts = [x0_h.pin_memory(), a0_h.pin_memory()]
+    shapes, dtypes = [shape, shape], [dt, dt]
+    if w["cond"]:
+        hosts.append(torch.randn(B, *w["cond"]).pin_memory())         # prompt embeddings travel with the batch (delete_sd.py)
+        shapes.append((B,) + tuple(w["cond"])); dtypes.append(torch.float32)
+    h2d = sum(t.numel() * t.element_size() for t in hosts) + B
+    host_out = torch.empty(5 + 16, dtype=torch.float32).pin_memory()
+    out_dev = torch.zeros(5 + 16, dtype=torch.float32, device=dev)
+    done = torch.cuda.Event()
+    feeder = DeviceFeeder(shapes, dtypes, dev, depth=2)
+    feeder.submit(hosts)                                              # batch 0: the pipeline's fill, outside the timed region
+    lo, hi = w["t_range"]
+    torch.manual_seed(42 + rank)
+
+    def cond_of(slot):
+        return {"encoder_hidden_states": slot[2]} if w["cond"] else None
+
+    def finish(st, bs):
+        host_out[:5].copy_(st, non_blocking=True)
+        host_out[5:].copy_(bs, non_blocking=True)
+        done.record()
+        done.synchronize()                                            # the loop reads its metrics every step
+
+    def eager_step(hook=None):
+        # dataset batch -> device (delete_celeb.py:560-564): this step's compute uses the batch submitted one step
+        # earlier; the copy of the NEXT batch (one per step) overlaps with it on the copy stream
+        slot = feeder.next()
+        if hook: hook("h2d_wait")
+        feeder.submit(hosts)
+        nz = torch.randn(shape, dtype=dt, device=dev)                 # :581
+        ts = torch.randint(lo, hi, (B,), device=dev).long()           # :593 / delete_tshirt.py:535
+        if hook: hook("torch_rng")
+        out = step.micro_step(slot[0], slot[1], nz, ts, conditioning=cond_of(slot))   # CPU Bernoulli draw + B bytes H2D inside
+        bs = batch_stats(out, D)                                      # :626-656 from the O(B) row sums (one launch)
+        if hook: hook("batch_stats")
+        st = step.sync_step()
+        if hook: hook("combine_k4")
+        finish(st, bs)
+        if hook: hook("d2h_and_sync")
+
+    step_rng = UnlearnStep(unet, sched, comb, device_rng=DeviceRng(seed=42, row_offset=rank * B), t_range=(lo, hi), **common)
+
+    def rng_step():
+        slot = feeder.next()
+        feeder.submit(hosts)
+        out = step_rng.micro_step(slot[0], slot[1], conditioning=cond_of(slot))
+        finish(step_rng.sync_step(), batch_stats(out, D))
+
+    def timed(fn, w_=None):
+        for _ in range(max(warmup, 3) if w_ is None else w_):
+            fn()
+        barrier()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(steps):
+            fn()
+        e_.record()
+        barrier()
+        el = torch.tensor([s_.elapsed_time(e_)], device=dev, dtype=torch.float64)
+        if n > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics: {host_out}"
+        return float(el.item()) / steps
+
+    eager_ms = timed(eager_step)
+    rng_ms = timed(rng_step, 3)
+
+    # ---- stage breakdown of the eager loop (a separate pass: each mark is one event record on the compute stream)
+    marks = []
+
+    def hook(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+
+    per_stage = {}
+    step.stage_hook = hook
+    for i in range(min(steps, 20) + 2):
+        marks.clear()
+        hook("start")
+        eager_step(hook)
+        torch.cuda.synchronize()
+        if i >= 2:
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                per_stage.setdefault(name, []).append(a.elapsed_time(b))
+    step.stage_hook = None
+    barrier()
+    breakdown = {k: statistics.median(v) for k, v in per_stage.items()}
+    stub = breakdown.get("unet_fwd", 0.0) + breakdown.get("backward_x", 0.0) + breakdown.get("backward_a", 0.0)
+    res = {"value": B * n / (eager_ms * 1e-3), "unit": UNIT, "ms_per_step": eager_ms,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_out.numel() * 4),
+           "breakdown_ms": breakdown, "breakdown_sum_ms": sum(breakdown.values()), "stub_unet_ms": stub,
+           "ms_per_step_minus_stub_unet": eager_ms - stub,
+           "breakdown_note": ("median CUDA-event intervals of a separately instrumented pass of the same loop: h2d_wait = the compute "
+                              "stream waiting for this batch's pinned copy (the copy itself overlaps the previous step), torch_rng = "
+                              "torch.randn + randint, k1k2 / k3 = the loss kernels, unet_fwd / backward_x / backward_a = the "
+                              "P-parameter stub UNet's own autograd (NOT the path), combine_k4 = K4a + K4b (N>1: the exchange), "
+                              "d2h_and_sync = 84 B device->host + event wait"),
+           "device_rng_variant": {"value": B * n / (rng_ms * 1e-3), "ms_per_step": rng_ms,
+                                  "note": "same loop with UnlearnStep(device_rng=DeviceRng(...)) — opt-in seed semantics"},
+           "api": "siss_b200.feed.DeviceFeeder (pinned H2D, double-buffered) + step.UnlearnStep.micro_step + "
+                  "batch_stats + sync_step (GradCombiner), BenchUNet(P) stub; D2H of 21 scalars + event sync per step"}
+
+    # ---- graph-captured variant (one process, one GPU: the whole optimiser step of a feeder slot is ONE graph launch)
+    if n == 1:
+        try:
+            step_g = UnlearnStep(unet, sched, comb, device_rng=DeviceRng(seed=42, device_counter=dev), t_range=(lo, hi), **common)
+
+            def body(slot):
+                out = step_g.micro_step(slot[0], slot[1], conditioning=cond_of(slot))
+                batch_stats(out, D, dest=out_dev[5:])
+                out_dev[:5].copy_(step_g.sync_step())
+
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for k in range(2):
+                    body(feeder.slots[k])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graphs = []
+            for k in range(2):
+                gk = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gk):
+                    body(feeder.slots[k])
+                graphs.append(gk)
+
+            def graph_step():
+                feeder.next()
+                k = feeder._in_use
+                feeder.submit(hosts)
+                graphs[k].replay()
+                host_out.copy_(out_dev, non_blocking=True)
+                done.record()
+                done.synchronize()
+
+            g_ms = timed(graph_step, 3)
+            res["graph_variant"] = {"value": B * n / (g_ms * 1e-3), "ms_per_step": g_ms,
+                                    "note": ("device-RNG loop with micro_step + batch_stats + sync_step captured as one CUDA graph per "
+                                             "feeder slot; H2D on the copy stream and the 84 B D2H + event sync stay outside the graph")}
+            del graphs
+        except Exception as e:  # supplementary: never lose the bench line
+            res["graph_variant"] = {"error": repr(e)}
+    del feeder, step, step_rng, comb, unet
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_siss(args):
     import torch.distributed as dist
     from siss_b200 import ops, _lib
@@ -617,14 +812,19 @@ def run_siss(args):
         resident_step()
     barrier()
     launches0 = ops.launch_count
-    sampler = ClockSampler(local_rank)
+    # clocks are reported for rank 0's GPU only, so only rank 0 polls NVML — and at 5 ms, not 2: NVML queries take driver
+    # locks, and 8 processes polling at 500 Hz stalled the copy-engine schedules' ~60 driver calls per exchange for tens
+    # of ms at a time (4.7 vs 2.0 ms/step at N = 4 with and without the sampler, gpurun_out/r2_gap4_*.json)
+    sampler = ClockSampler(local_rank if (rank == 0 and os.environ.get("SISS_BENCH_NO_NVML") != "1") else -1)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler:
         # timed region 1: exactly K steps, no per-kernel instrumentation -> `value`
+        t_host0 = time.perf_counter()
         start.record()
         for _ in range(args.steps):
             resident_step()
         end.record()
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # how long the HOST needs to enqueue a step
         barrier()
         gpu_launches = ops.launch_count - launches0
         # timed region 2: the same K steps again with a CUDA-event bracket around every kernel launch ->
@@ -769,7 +969,7 @@ def run_siss(args):
                                  "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/; "
                                  "copy_same_bytes_ms = a plain D2D copy moving the kernel's algorithmic bytes under the same "
                                  "bracket with L2 flushed (the floor at that size), vs_copy_same_bytes = that / kernel ms"),
-                "kernel_share_of_step": share,
+                "kernel_share_of_step": share, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "l2_note": ("siss_combine re-reads what siss_norm3 just streamed; siss_norm3 leaves the last SISS_L2_KEEP_MB "
                             "(default 80) MB of the buffers in L2 with an evict_last policy and the combine walks in reverse, so "
                             "~6 % of its algorithmic bytes never reach DRAM and frac may exceed 1. `traffic` is an ncu capture, "
@@ -778,100 +978,17 @@ def run_siss(args):
     # ---------------------------------------------------------------- e2e arm (public API, host buffers)
     e2e = None
     if not args.no_e2e:
-        del G_out, pred
-        torch.cuda.empty_cache()
-        unet = BenchUNet(P).to(dev)
-        del G_x, G_a
+        del G_out, pred, G_x, G_a, x0, a0
         comb = None
         holder = None
         torch.cuda.empty_cache()
-        comb = GradCombiner(unet.parameters(), transport=args.transport)
-        step = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B * n,
-                           lambd=lambd, scaling_norm=scaling_norm, max_norm=max_norm)
-        from siss_b200.feed import DeviceFeeder
-        x0_p, a0_p = x0_h.pin_memory(), a0_h.pin_memory()
-        host_out = torch.empty(5 + 16, dtype=torch.float32).pin_memory()
-        done = torch.cuda.Event()
-        torch.manual_seed(42 + rank)
-        del x0, a0
-        feeder = DeviceFeeder([shape, shape], [dt, dt], dev, depth=2)
-        feeder.submit([x0_p, a0_p])                           # batch 0 (outside the timed region: the pipeline's fill)
-
-        def e2e_step():
-            # dataset batch -> device (delete_celeb.py:560-564): this step's compute uses the batch submitted
-            # one step earlier; the copy of the NEXT batch (one per step, 2*B*D*s bytes) overlaps with it
-            x0, a0 = feeder.next()
-            feeder.submit([x0_p, a0_p])
-            nz = torch.randn(shape, dtype=dt, device=dev)     # :581
-            ts = torch.randint(999, 1000, (B,), device=dev).long()   # :593
-            out = step.micro_step(x0, a0, nz, ts)             # CPU Bernoulli draw + 64 B H2D inside
-            bs = batch_stats(out, D)                          # :626-656 from the O(B) row sums (one launch)
-            st = step.sync_step()
-            host_out[:5].copy_(st, non_blocking=True)
-            host_out[5:].copy_(bs, non_blocking=True)
-            done.record()
-            done.synchronize()                                # the loop reads its metrics every step
-            return host_out
-
-        for _ in range(max(args.warmup, 3)):
-            e2e_step()
-        barrier()
-        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e2.record()
-        barrier()
-        el2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el2, op=dist.ReduceOp.MAX)
-        e2e_ms = float(el2.item())
-        assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics: {host_out}"
-        # supplementary: the same loop with the opt-in device RNG (eps generated inside K1oK2, t and the Bernoulli mask
-        # drawn on the device: no torch.randn / randint launches, no CPU mask + H2D)
-        from siss_b200.rng import DeviceRng
-        step_rng = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=B * n,
-                               lambd=lambd, scaling_norm=scaling_norm, max_norm=max_norm,
-                               device_rng=DeviceRng(seed=42, row_offset=rank * B), t_range=(999, 1000))
-
-        def e2e_step_rng():
-            x0, a0 = feeder.next()
-            feeder.submit([x0_p, a0_p])
-            out = step_rng.micro_step(x0, a0)
-            bs = batch_stats(out, D)
-            st = step_rng.sync_step()
-            host_out[:5].copy_(st, non_blocking=True)
-            host_out[5:].copy_(bs, non_blocking=True)
-            done.record()
-            done.synchronize()
-
-        for _ in range(3):
-            e2e_step_rng()
-        barrier()
-        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s3.record()
-        for _ in range(args.steps):
-            e2e_step_rng()
-        e3.record()
-        barrier()
-        el3 = torch.tensor([s3.elapsed_time(e3)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el3, op=dist.ReduceOp.MAX)
-        rng_ms = float(el3.item())
-        assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics (device rng): {host_out}"
-        e2e_rng = {"value": B * n * args.steps / (rng_ms / 1e3), "ms_per_step": rng_ms / args.steps,
-                   "note": "SUPPLEMENTARY: same e2e loop with UnlearnStep(device_rng=DeviceRng(...)) — opt-in seed semantics"}
-        e2e = {"value": B * n * args.steps / (e2e_ms / 1e3), "unit": UNIT, "device_rng_variant": e2e_rng,
-               "h2d_bytes_per_step": int(2 * B * D * s_in + B), "d2h_bytes_per_step": int(host_out.numel() * 4),
-               "ms_per_step": e2e_ms / args.steps,
-               "api": "siss_b200.feed.DeviceFeeder (pinned H2D, double-buffered) + step.UnlearnStep.micro_step + "
-                      "batch_stats + sync_step (GradCombiner), BenchUNet(P) stub; D2H of 21 scalars + event sync per step"}
+        e2e = measure_e2e(celeb_workload(args), dev, n, rank, args.steps, args.warmup, args.transport, barrier, dist)
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1)
     cpu_baseline = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()
-        times, threads = time_cpu(args, args.cpu_steps, 1)
+        times, threads = time_cpu(celeb_workload(args), args.cpu_steps, 1)
         med = statistics.median(times)
         cpu_baseline = {"value": B / med, "unit": UNIT, "cores": threads, "kind": "port",
                         "ms_per_step": med * 1e3,
@@ -890,6 +1007,24 @@ def run_siss(args):
     if rank == 0 and n == 1 and not args.no_extra_configs:
         torch.cuda.empty_cache()
         others = extra_configs(dev)
+        for wl, cpu_steps in ((TSHIRT, 40), (SD, 2)):
+            key = next((k for k in others if k.startswith(wl["name"] + ":")), wl["name"])
+            entry = others.setdefault(key, {})
+            try:
+                torch.cuda.empty_cache()
+                entry["e2e"] = measure_e2e(wl, dev, 1, 0, min(args.steps, 30), 3, "auto", barrier, dist)
+            except Exception as e:
+                entry["e2e"] = {"error": repr(e)}
+            if not args.no_cpu_baseline:
+                try:
+                    times, threads = time_cpu(wl, cpu_steps, 1)
+                    med = statistics.median(times)
+                    entry["cpu_baseline"] = {"value": wl["B"] / med, "unit": UNIT, "cores": threads, "kind": "port",
+                                             "ms_per_step": med * 1e3,
+                                             "sample": (f"full workload per step (B={wl['B']}, P={wl['P']}), median of {len(times)} "
+                                                        "steps after 1 warm-up, oracle port of the reference loop in torch CPU")}
+                except Exception as e:
+                    entry["cpu_baseline"] = {"error": repr(e)}
         try:
             eager_ref = eager_gpu_reference(args, dev)
         except Exception as e:  # supplementary: never break the bench line
@@ -905,7 +1040,12 @@ def run_siss(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
             "roofline": roofline, "comm": comm, "exchange_check": exchange_check,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": sampler.summary(), "unlearn_steps": unlearn, "other_configs": others,
+            "clocks": sampler.summary(), "unlearn_steps": unlearn,
+            "unlearn_steps_real_unet": ("UNMEASURED: the second half of BASELINE's metric (unlearn steps/s @1/2/4/8 with the "
+                                        "diffusers UNet2DModel / SD UNet) cannot be measured in this image — diffusers is not "
+                                        "installed and there is no network; `unlearn_steps` uses a stand-in conv UNet with the "
+                                        "real parameter count and ~100x fewer FLOPs"),
+            "other_configs": others,
             "eager_gpu_reference": eager_ref,
         }
         emit(line)

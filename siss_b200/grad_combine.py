@@ -167,8 +167,9 @@ class GradCombiner:
         self.tuning = res
         best_peer_full = res.get(self.peer.algo, float("inf"))
         best_peer_xpre = res.get(self.peer.algo_xpre + "+xpre", float("inf"))
-        self._nccl_full = res.get("nccl", float("inf")) < best_peer_full
-        self._nccl_xpre = res.get("nccl+xpre", float("inf")) < best_peer_xpre
+        # NCCL must beat the fused kernels by more than the tuning margin (ties go to the kernels we control)
+        self._nccl_full = res.get("nccl", float("inf")) < best_peer_full * 0.97
+        self._nccl_xpre = res.get("nccl+xpre", float("inf")) < best_peer_xpre * 0.97
         self.transport = "nccl" if self._nccl_full else self.peer.algo
         self.stats.zero_()
 

@@ -44,6 +44,21 @@ NEEDS_MULTICAST = ("nvls",) + PIPELINED
 CE_CHUNKS = max(1, min(16, int(os.environ.get("SISS_CE_CHUNKS", "4"))))
 
 
+# Preference order of the schedules when their measured times are within TUNE_MARGIN of each other: the simplest and
+# most deterministic first (rank-ordered sums, fewest host calls), the copy-engine schedules — ~60 driver calls per
+# exchange, the most exposed to host / driver jitter — last. A later schedule must be more than 3 % faster to be chosen.
+PREFERENCE = ("p2p", "nvls", "pipe", "pipe_nvls", "ce", "pipe_ce")
+TUNE_MARGIN = 0.03
+
+
+def _pick(times: Dict[str, float]) -> str:
+    best = None
+    for name in PREFERENCE:
+        if name in times and (best is None or times[name] < times[best] * (1.0 - TUNE_MARGIN)):
+            best = name
+    return best if best is not None else min(times, key=times.get)
+
+
 class PeerExchange:
     def __init__(self, total: int, device: torch.device, group: Optional[dist.ProcessGroup] = None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -228,7 +243,7 @@ class PeerExchange:
         ops._count(2)
 
     # ------------------------------------------------------------------------------------------
-    def tune(self, extra: Optional[Dict[str, Callable[[bool], None]]] = None, iters: int = 4,
+    def tune(self, extra: Optional[Dict[str, Callable[[bool], None]]] = None, iters: int = 7,
              candidates: Optional[Sequence[str]] = None) -> Dict[str, float]:
         """Measure every available schedule on the real buffers (CUDA events, max over ranks) and adopt the fastest
         for (a) the full exchange and (b) the exchange with G_x already reduced. ``extra`` adds competitors that are
@@ -256,13 +271,14 @@ class PeerExchange:
             fn()
             torch.cuda.synchronize(dev)
             dist.barrier(group=self.group)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(iters):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+            evs[0].record()
+            for i in range(iters):
                 fn()
-            e.record()
+                evs[i + 1].record()
             torch.cuda.synchronize(dev)
-            times[j] = s.elapsed_time(e) / iters
+            per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
+            times[j] = per[len(per) // 2] if len(per) % 2 else 0.5 * (per[len(per) // 2 - 1] + per[len(per) // 2])   # median: immune to one stall
         dist.all_reduce(times, op=dist.ReduceOp.MAX, group=self.group)
         self.g_x.zero_(); self.g_a.zero_()
         torch.cuda.synchronize(dev)
@@ -271,11 +287,11 @@ class PeerExchange:
         own_full = {k: v for k, v in res.items() if k in ALGOS}
         own_xpre = {k[:-5]: v for k, v in res.items() if k.endswith("+xpre") and k[:-5] in THREE_STAGE}
         if own_full:
-            self.algo = min(own_full, key=own_full.get)
+            self.algo = _pick(own_full)
             three = {k: v for k, v in own_full.items() if k in THREE_STAGE}
             if three:
-                self.algo3 = min(three, key=three.get)
+                self.algo3 = _pick(three)
         if own_xpre:
-            self.algo_xpre = min(own_xpre, key=own_xpre.get)
+            self.algo_xpre = _pick(own_xpre)
         self.tuning = res
         return res

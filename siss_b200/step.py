@@ -26,7 +26,7 @@ from .grad_combine import GradCombiner
 from .losses.ddpm_deletion_loss import _draw_keep_mask
 from .scheduler import SissDDPMScheduler
 
-TWO_TERM = ("importance_sampling_with_mixture", "double_forward_with_neg_del", "erasediff")
+TWO_TERM = ("importance_sampling_with_mixture", "double_forward_with_neg_del", "erasediff", "subscore_bernoulli")
 ONE_TERM = ("naive_del", "simple_neg_del")
 
 
@@ -57,13 +57,14 @@ class UnlearnStep:
             raise ValueError(f"unknown loss_fn {loss_fn!r}")
         if superfactor_decay_on not in ("micro_step", "sync_step"):
             raise ValueError('superfactor_decay_on must be "micro_step" or "sync_step"')
-        if loss_fn == "importance_sampling_with_mixture" and lambd is None:
-            raise ValueError("importance_sampling_with_mixture needs lambd")
+        if loss_fn in ("importance_sampling_with_mixture", "subscore_bernoulli") and lambd is None:
+            raise ValueError(f"{loss_fn} needs lambd")
         if loss_fn == "simple_neg_del" and superfactor is None:
             raise ValueError("simple_neg_del needs superfactor")
         if loss_fn == "erasediff" and eta is None:
             raise ValueError("erasediff needs eta")
-        if loss_fn in ("importance_sampling_with_mixture", "double_forward_with_neg_del") and scaling_norm is None:
+        if loss_fn in ("importance_sampling_with_mixture", "double_forward_with_neg_del", "subscore_bernoulli") \
+                and scaling_norm is None:
             raise ValueError(f"{loss_fn} needs scaling_norm")
         self.unet, self.scheduler, self.combiner = unet, scheduler, combiner
         self.loss_fn = loss_fn
@@ -83,6 +84,10 @@ class UnlearnStep:
         self.gamma, self.sigma = scheduler.gamma_sigma(dev)
         self._micro = 0
         self.device_rng = device_rng
+        # optional profiling callback: called with a stage name on the current stream right after each stage of a
+        # micro-step has been enqueued ("k1k2", "unet_fwd", "k3", "backward_x", "backward_a"); bench.py records CUDA
+        # events in it to decompose the end-to-end step. None (the default) costs nothing.
+        self.stage_hook: Optional[Callable[[str], None]] = None
         self.t_range = (0, int(self.gamma.numel())) if t_range is None else (int(t_range[0]), int(t_range[1]))
 
     # ------------------------------------------------------------------------------------------
@@ -101,6 +106,8 @@ class UnlearnStep:
         noise, timesteps, keep_mask, draw = self._device_draws(x0, noise, timesteps, keep_mask, siss, out)
         if siss:
             self._micro_siss(x0, a0, noise, timesteps, keep_mask, cond, draw, last, out)
+        elif self.loss_fn == "subscore_bernoulli":
+            self._micro_subscore(x0, a0, noise, timesteps, keep_mask, cond, last, out)
         elif self.loss_fn in ("double_forward_with_neg_del", "erasediff"):
             draw = self._micro_two_forward(x0, a0, noise, timesteps, forget_target, cond, draw, last, out)
         else:
@@ -111,6 +118,10 @@ class UnlearnStep:
             self.device_rng.advance()      # next micro-step draws from the next index (host mirror + device counter)
         self._micro += 1
         return out
+
+    def _stage(self, name: str) -> None:
+        if self.stage_hook is not None:
+            self.stage_hook(name)
 
     def _device_draws(self, x0, noise, timesteps, keep_mask, siss: bool, out: Dict[str, torch.Tensor]):
         """Opt-in device RNG: fill in whatever of (timesteps, keep mask, eps) the caller left out. For SISS eps stays
@@ -143,14 +154,50 @@ class UnlearnStep:
         else:
             x_mix, d_x, d_a, w_x, w_a = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod,
                                                               self.gamma, self.sigma, self.lambd)
+        self._stage("k1k2")
         pred = self.unet(x_mix, timesteps, **cond, return_dict=False)[0]
+        self._stage("unet_fwd")
         g_x, g_a, rl_x, rl_a = ops.wmse_fwd_bwd(pred.detach(), x_mix, x0, a0, timesteps, self.gamma, self.sigma,
                                                 w_x, w_a, self.go, self.go)
+        self._stage("k3")
         cb.begin_x()
         torch.autograd.backward(pred, g_x, retain_graph=True)
+        self._stage("backward_x")
         cb.begin_a(last_micro_step=last)      # data parallel: G_x's reduce-scatter overlaps backward #2
         torch.autograd.backward(pred, g_a)
+        self._stage("backward_a")
         out.update(w_x=w_x, w_a=w_a, dist_x=d_x, dist_a=d_a, row_loss_x=rl_x, row_loss_a=rl_a)
+
+    def _micro_subscore(self, x0, a0, noise, timesteps, keep_mask, cond, last: bool, out) -> None:
+        """subscore_bernoulli (ddpm_deletion_loss.py:99-122; only delete_tshirt.py runs it through the two-backward block,
+        with retain_graph, :632): Bernoulli row select of the two noisy batches (the select of K1oK2; its weights are not
+        used), ONE forward, squared error against the shared eps; the keep rows — scaled by the Python float 1/(1-lambd)
+        — form the first term, the forget rows the second. In autograd's order that is, per element,
+            keep row:    dL_x = fp32(go * fp32(1/(1-lambd))) * (2 u),   dL_a = 0
+            forget row:  dL_x = 0,                                     dL_a = go * (2 u),      u = eps_hat - eps
+        which the dual-MSE kernel evaluates for all rows with the two scalars; the row masks are applied to its outputs.
+        The reference's zero-row fallbacks (:113-120) replace BOTH terms by constants when no keep row was drawn and the
+        second term when no forget row was drawn — i.e. zero gradients, reproduced here on the device without a sync."""
+        cb = self.combiner
+        coef = 1 / (1 - self.lambd)        # ZeroDivisionError at lambd == 1, exactly like the reference (:111)
+        keep = _draw_keep_mask(x0.shape[0], self.lambd) if keep_mask is None else keep_mask
+        x_sel, *_ = ops.add_noise_mixture(x0, a0, noise, keep, timesteps, self.alphas_cumprod, self.gamma, self.sigma,
+                                          self.lambd)
+        pred = self.unet(x_sel, timesteps, **cond, return_dict=False)[0]
+        go_x = float(np.float32(self.go) * np.float32(coef))
+        p = pred.detach()
+        tgt = noise if noise.dtype == p.dtype or p.dtype == torch.float32 else noise.to(torch.promote_types(noise.dtype, p.dtype))
+        g_x, g_a, rl, _ = ops.dual_mse_fwd_bwd(p, p, tgt, tgt, go_x, self.go)
+        m = keep.to(device=p.device, dtype=torch.bool).view(-1, *([1] * (p.dim() - 1)))
+        any_keep = m.any()
+        zero = torch.zeros((), dtype=g_x.dtype, device=p.device)
+        g_x = torch.where(m, g_x, zero)
+        g_a = torch.where(m | ~any_keep, zero, g_a)
+        cb.begin_x()
+        torch.autograd.backward(pred, g_x, retain_graph=True)
+        cb.begin_a(last_micro_step=last)
+        torch.autograd.backward(pred, g_a)
+        out.update(row_loss=rl, keep_mask=m.view(-1))
 
     def _micro_two_forward(self, x0, a0, noise, timesteps, forget_target, cond, draw, last: bool, out):
         """double_forward_with_neg_del / erasediff: K1 pair -> two UNet forwards -> dual-MSE kernel -> two backward passes.

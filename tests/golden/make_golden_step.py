@@ -56,6 +56,7 @@ CASES = [
     dict(name="step_erasediff_G2_celeb", task="delete_celeb", loss_fn="erasediff", G=2, eta=0.05),
     dict(name="step_naive_G2_celeb", task="delete_celeb", loss_fn="naive_del", G=2),
     dict(name="step_neggrad_G1_tshirt", task="delete_tshirt", loss_fn="simple_neg_del", G=1, superfactor=0.7),
+    dict(name="step_subscore_G2_tshirt", task="delete_tshirt", loss_fn="subscore_bernoulli", G=2, lambd=0.4, scaling_norm=5.0),
 ]
 
 
@@ -85,7 +86,7 @@ def main():
             torch.manual_seed(draw_seed)
             items = getattr(loss_obj, fn)(net, t, noise, {}, all_d, del_d, **kwargs)
             torch.manual_seed(draw_seed)                       # replay the method's own RNG draw
-            if fn == "importance_sampling_with_mixture":
+            if fn in ("importance_sampling_with_mixture", "subscore_bernoulli"):
                 data[f"keep/{k}"] = (torch.rand(B) > c["lambd"]).numpy()
             elif fn == "erasediff":
                 data[f"forget_target/{k}"] = torch.rand_like(noise).numpy()

@@ -138,6 +138,7 @@ class TinyNet(torch.nn.Module):
     ("double_forward_with_neg_del", dict(scaling_norm=500.0)),
     ("naive_del", dict()),
     ("simple_neg_del", dict(superfactor=0.3)),
+    ("subscore_bernoulli", dict(lambd=0.5, scaling_norm=5.0)),
 ])
 @pytest.mark.parametrize("G", [1, 3])
 def test_unlearn_step_matches_reference_loop(loss_fn, kw, G, dev):
@@ -166,15 +167,19 @@ def test_unlearn_step_matches_reference_loop(loss_fn, kw, G, dev):
         all_d = {"og_latents": x0, "noisy_latents": O.add_noise(sched.alphas_cumprod, x0, noise, t)}
         del_d = {"og_latents": a0, "noisy_latents": O.add_noise(sched.alphas_cumprod, a0, noise, t)}
         okw = {}
-        if loss_fn == "importance_sampling_with_mixture":
+        if loss_fn in ("importance_sampling_with_mixture", "subscore_bernoulli"):
+            if loss_fn == "subscore_bernoulli" and k == G - 1 and G > 1:
+                keep = torch.ones(B, dtype=torch.bool)             # no forget row drawn: the second term is a constant
             okw = dict(lambd=0.5, keep_mask=keep)
         elif loss_fn == "simple_neg_del":
             okw = dict(superfactor=0.3)
         items = getattr(oloss, loss_fn)(cpu_net, t, noise, {}, all_d, del_d, **okw)
-        loop.micro_step(items, retain_graph=(loss_fn == "importance_sampling_with_mixture"))
+        loop.micro_step(items, retain_graph=(loss_fn in ("importance_sampling_with_mixture", "subscore_bernoulli")))
         out = step.micro_step(x0.to(dev), a0.to(dev), noise.to(dev), t.to(dev), keep_mask=keep)
         if items[1] is not None and "row_loss_x" in out:
             torch.testing.assert_close(out["row_loss_x"].cpu(), items[1].detach().sum(dim=[1, 2, 3]), rtol=1e-4, atol=1e-5)
+        if loss_fn == "subscore_bernoulli":
+            assert torch.equal(out["keep_mask"].cpu(), keep)
     assert step.is_sync_step
     single = loss_fn in ("naive_del", "simple_neg_del")
     ref = loop.sync_step(single, loss_fn, scaling_norm=kw.get("scaling_norm"), max_norm=1.0)
