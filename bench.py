@@ -624,7 +624,10 @@ def measure_e2e(w, dev, n, rank, steps, warmup, transport, barrier, dist):
         el = torch.tensor([s_.elapsed_time(e_)], device=dev, dtype=torch.float64)
         if n > 1:
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        assert bool(torch.isfinite(host_out).all()), f"non-finite e2e statistics: {host_out}"
+        # B = 1 (delete_sd) makes the reference's unbiased per-batch std NaN by construction (delete_celeb.py:640-656);
+        # everything else — the five gradient scalars and the means / extrema — must be finite
+        chk = host_out if B > 1 else torch.cat([host_out[:5], host_out[5::4], host_out[6::4], host_out[7::4]])
+        assert bool(torch.isfinite(chk).all()), f"non-finite e2e statistics: {host_out}"
         return float(el.item()) / steps
 
     eager_ms = timed(eager_step)
