@@ -184,7 +184,7 @@ def synth_images(shape, dtype, seed):
 
 
 # --------------------------------------------------------------------------------------------------
-# clocks (NVML sampled in a thread during the timed region)
+# clocks (NVML, explicit samples while the GPU is under load: just before and inside the timed region)
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
@@ -212,30 +212,33 @@ class ClockSampler:
             self.nv = None
             self.err = repr(e)
 
-    def _run(self):
+    def _sample(self):
         nv = self.nv
-        while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
-                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if bits & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.005)
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    # NO polling thread (round 1 polled NVML at 500 Hz from every rank): an NVML query takes driver locks, and on a rank
+    # that is exchanging gradients over NVLink each one stalled the pipeline by ~1 ms — 4 samples cost the 50-step N = 2
+    # run 7 % (1.37 vs 1.28 ms/step with / without, gpurun_out/r2_nvml2_*.json), and 8 ranks polling stalled the
+    # copy-engine schedule for tens of ms. Instead the caller takes explicit samples at moments when the GPU is known
+    # to be under load: after the warm-up steps have been enqueued, and after the last timed step has been enqueued
+    # (the host runs ahead of the device, so the GPU is inside the timed region at that moment).
+    def sample_now(self):
+        if self.nv is not None:
+            self._sample()
 
     def __enter__(self):
-        if self.nv is not None:
-            self._thr = threading.Thread(target=self._run, daemon=True)
-            self._thr.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self._thr is not None:
-            self._thr.join(timeout=2)
+        pass
 
     def summary(self):
         if not self.samples:
@@ -814,6 +817,8 @@ def run_siss(args):
     for _ in range(max(args.warmup, 3)):
         resident_step()
     barrier()
+    for _ in range(3):
+        resident_step()                         # keep the GPU under load while the clocks are read (outside the timed region)
     launches0 = ops.launch_count
     # clocks are reported for rank 0's GPU only, so only rank 0 polls NVML — and at 5 ms, not 2: NVML queries take driver
     # locks, and 8 processes polling at 500 Hz stalled the copy-engine schedules' ~60 driver calls per exchange for tens
@@ -821,6 +826,8 @@ def run_siss(args):
     sampler = ClockSampler(local_rank if (rank == 0 and os.environ.get("SISS_BENCH_NO_NVML") != "1") else -1)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler:
+        sampler.sample_now()                    # GPU busy with the three extra warm-up steps above
+        barrier()
         # timed region 1: exactly K steps, no per-kernel instrumentation -> `value`
         t_host0 = time.perf_counter()
         start.record()
@@ -828,6 +835,7 @@ def run_siss(args):
             resident_step()
         end.record()
         host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # how long the HOST needs to enqueue a step
+        sampler.sample_now()                    # the host runs ahead: the GPU is still inside the timed steps here
         barrier()
         gpu_launches = ops.launch_count - launches0
         # timed region 2: the same K steps again with a CUDA-event bracket around every kernel launch ->
