@@ -294,4 +294,6 @@ class PeerExchange:
         if own_xpre:
             self.algo_xpre = _pick(own_xpre)
         self.tuning = res
+        if not any(a in ("ce", "pipe_ce") for a in (self.algo, self.algo_xpre, self.algo3)):
+            self._staging = None           # the DMA landing area (2 (N-1)/N P floats) is only kept if a DMA schedule won
         return res
