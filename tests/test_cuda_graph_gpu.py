@@ -138,15 +138,10 @@ def test_device_rng_draws_fresh_values_on_every_graph_replay(cuda_device, loss_f
     assert not torch.equal(eager[0][0], eager[1][0]) and not torch.equal(eager[1][2], eager[2][2])   # draws do differ
 
     net_g, step_g = make(True)
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        one(step_g)                                      # draw 0, eagerly
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        ts_static, gs_static = one(step_g)               # captured while the device counter reads 1
+    from siss_b200.graph import CapturedStep
+    captured = CapturedStep(lambda: one(step_g), warmup=1)     # draw 0 eagerly (side stream), then captured while the
+    ts_static, gs_static = captured.outputs                    # device counter reads 1
+    graph = captured.graph
     for k in (1, 2, 3):
         graph.replay()
         torch.cuda.synchronize()
