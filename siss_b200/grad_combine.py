@@ -24,6 +24,7 @@ runs K4b on the shard and all-gathers the result.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -136,6 +137,27 @@ class GradCombiner:
         self._combine = ops.combine
         if self.world > 1 and transport == "auto" and self.peer is not None:
             self._autotune()
+        # Overlap of the G_a reduce with the second backward pass (peer / multicast / DMA transports): see begin_a().
+        self._early_a = False          # this optimiser step's G_a reduce is being issued shard by shard on the side stream
+        self._armed = False
+        self._overlap = (self.peer is not None and os.environ.get("SISS_NO_OVERLAP") != "1")
+        if self._overlap:
+            S = self.shard_len
+            self._param_shards = [list(range(o // S, min((o + max(p.numel(), 1) - 1) // S, self.world - 1) + 1))
+                                  for o, p in zip(self.offsets, self.params)]
+            self._shard_nparams = [0] * self.world
+            for ks in self._param_shards:
+                for k in ks:
+                    self._shard_nparams[k] += 1
+            import weakref
+            me = weakref.ref(self)                 # the hooks must not keep a discarded combiner (and its buffers) alive
+
+            def _hook(_p, i):
+                cb = me()
+                if cb is not None:
+                    cb._on_grad(i)
+            for i, prm in enumerate(self.params):
+                prm.register_post_accumulate_grad_hook(lambda _p, i=i: _hook(_p, i))
         self._point(self._views_x)   # start out accumulating into G_x (needed by the after_backward_* spelling)
 
     # ------------------------------------------------------------------------------------------
@@ -205,6 +227,17 @@ class GradCombiner:
                 dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
                 self._early_done.record(self._side)
             self._early_x = True
+            if self._overlap and not self._nccl_xpre:
+                # ... and G_a's reduce follows it on the same side stream, shard by shard, UNDER backward #2: a
+                # post-accumulate hook on every parameter counts down the parameters overlapping each rank's shard of the
+                # flat buffer; as soon as shard k (k = world-1 .. 0: autograd finishes the last-registered parameters
+                # first) is final, every rank enqueues a barrier for it and its owner launches the first-stage kernel
+                # (PeerExchange.early_reduce_a). Whatever has not fired by the time the exchange is called (parameters
+                # without a gradient, the first-registered layers) is flushed there, in the same order on every rank.
+                self._pending = list(self._shard_nparams)
+                self._next_shard = self.world - 1
+                self._armed = True
+                self._early_a = True
 
     # The same protocol in the "after" spelling SURVEY.md §8b sketches for this boundary: nothing to call before the
     # first backward of a micro-step (the combiner starts out, and is left by after_backward_a / zero_grad /
@@ -252,19 +285,48 @@ class GradCombiner:
         self._point(self._views_x)
         return self.stats
 
+    def _on_grad(self, i: int) -> None:
+        """post-accumulate-grad hook of parameter i (runs on autograd's thread while backward() blocks the caller)."""
+        if not self._armed:
+            return
+        for k in self._param_shards[i]:
+            self._pending[k] -= 1
+        self._issue_ready(torch.cuda.current_stream(self.device))
+
+    def _issue_ready(self, producer: torch.cuda.Stream, flush: bool = False) -> None:
+        while self._next_shard >= 0 and (flush or self._pending[self._next_shard] <= 0):
+            ev = torch.cuda.Event()
+            ev.record(producer)                   # the accumulation that completed this shard is enqueued before this point
+            self._side.wait_event(ev)
+            self.peer.early_reduce_a(self._next_shard, self._side)
+            self._next_shard -= 1
+
+    def _finish_early_a(self) -> None:
+        """Called when the exchange starts: flush the shards whose hooks have not fired, then order the caller's stream
+        after the side stream. From here on the first stage of the exchange is done."""
+        cur = torch.cuda.current_stream(self.device)
+        self._issue_ready(cur, flush=True)
+        self._armed = False
+        self._early_done.record(self._side)
+        cur.wait_event(self._early_done)
+
     def exchange(self, mode: int, value: float, max_norm: float, inf_guard: bool = False) -> torch.Tensor:
         """Data parallel only — the exchange step by itself: sum ``G_x`` / ``G_a`` over the ranks, K4a, K4b, result in
         every rank's ``G_x``; through whichever transport was chosen (fused peer / multicast kernels or NCCL collectives).
         Does NOT clear ``G_a`` or touch ``param.grad`` (that is :meth:`combine`). Returns the device stats tensor."""
         if self.world == 1:
             raise RuntimeError("exchange() is a data-parallel step")
-        if self._early_x:
+        if self._early_a:
+            self._finish_early_a()
+        elif self._early_x:
             torch.cuda.current_stream(self.device).wait_event(self._early_done)
         use_nccl = self._nccl_xpre if self._early_x else self._nccl_full
         if use_nccl:
             self._nccl_exchange(mode, value, max_norm, inf_guard, self._early_x)
         else:
-            self.peer.combine(mode, value, max_norm, inf_guard, self.stats, x_prereduced=self._early_x)
+            self.peer.combine(mode, value, max_norm, inf_guard, self.stats, x_prereduced=self._early_x,
+                              reduced=self._early_a)
+        self._early_a = False
         return self.stats
 
     def wire_bytes(self, x_prereduced: bool = False) -> Dict[str, object]:

@@ -161,14 +161,17 @@ class FusedCombineAdamW:
                 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
                 _lib.check(_lib.load().siss_counter_add(ctypes.c_void_p(self.d_step.data_ptr()), 1, stream), "siss_counter_add")
                 ops._count()
-                if cb._early_x:
+                if cb._early_a:
+                    cb._finish_early_a()          # G_a's first stage ran shard by shard under backward #2
+                elif cb._early_x:
                     torch.cuda.current_stream(cb.device).wait_event(cb._early_done)
                 mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF
                 cb.peer.adamw_allgather(mode, float(scaling_norm if eta is None else eta), mn, inf_guard, cb.stats,
                                         self.exp_avg, self.exp_avg_sq, self.ema_flat, self.lr, self.betas, self.eps,
                                         self.weight_decay, self.step_count, self.d_step, self.d_sched,
-                                        self.cur_ema_decay, x_prereduced=cb._early_x)
+                                        self.cur_ema_decay, x_prereduced=cb._early_x, reduced=cb._early_a)
                 cb._early_x = False
+                cb._early_a = False
                 cb.g_x.zero_(); cb.g_a.zero_()
                 cb._dirty_x = False
                 cb._point(cb._views_x)

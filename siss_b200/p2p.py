@@ -42,6 +42,9 @@ PIPELINED = ("pipe", "pipe_nvls", "pipe_ce")
 ALGOS = THREE_STAGE + PIPELINED
 NEEDS_MULTICAST = ("nvls",) + PIPELINED
 CE_CHUNKS = max(1, min(16, int(os.environ.get("SISS_CE_CHUNKS", "4"))))
+# every rank-to-rank barrier kernel gives up (device-side trap -> CUDA error) after this long instead of spinning for
+# ever: a rank that died or took another code path must not leave its peers' GPUs hung
+BARRIER_TIMEOUT_MS = int(os.environ.get("SISS_BARRIER_TIMEOUT_MS", "120000"))
 
 
 # Preference order of the schedules when their measured times are within TUNE_MARGIN of each other: the simplest and
@@ -167,7 +170,7 @@ class PeerExchange:
                         exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, ema_shard: Optional[torch.Tensor],
                         lr: float, betas, eps: float, weight_decay: float, step: int, d_step: torch.Tensor,
                         d_sched: Optional[torch.Tensor], ema_decay: float, x_prereduced: bool = False,
-                        algo: Optional[str] = None) -> None:
+                        algo: Optional[str] = None, reduced: bool = False) -> None:
         """Two-term sync step with the ZeRO-1 update: reduce kernel as in :meth:`combine`, then K4b + AdamW/EMA on this
         rank's shard + parameter all-gather (peer stores or one multicast store per vector). New parameters land in
         every rank's ``p_flat``. Three-stage schedules only. Stream-ordered; no host synchronisation."""
@@ -179,9 +182,10 @@ class PeerExchange:
         if algo == "nvls" and not (self.has_multicast and self.mc_p):
             algo = "p2p"
         # "ce": DMA reduce, then the peer-store kernel for the fused update + parameter all-gather
-        self.h_x.barrier(channel=0)
-        self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
-        self.h_x.barrier(channel=1)
+        if not reduced:
+            self.h_x.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)
+            self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
+        self.h_x.barrier(channel=1, timeout_ms=BARRIER_TIMEOUT_MS)
         tail = (int(mode), float(value), float(max_norm), int(bool(inf_guard)),
                 P(exp_avg.data_ptr()), P(exp_avg_sq.data_ptr()), float(lr), float(betas[0]), float(betas[1]), float(eps),
                 float(weight_decay), int(step), P(d_step.data_ptr()), P(0 if d_sched is None else d_sched.data_ptr()),
@@ -194,35 +198,54 @@ class PeerExchange:
             _lib.check(lib.siss_p2p_adamw_allgather(
                 self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), self.ptrs_p, self.world,
                 self.rank, self.shard_len, *tail), "siss_p2p_adamw_allgather")
-        self.h_x.barrier(channel=2)        # every rank's parameter shard has landed in every p_flat
+        self.h_x.barrier(channel=2, timeout_ms=BARRIER_TIMEOUT_MS)        # every rank's parameter shard has landed in every p_flat
         ops._count(2)
 
+    def early_reduce_a(self, shard: int, stream: torch.cuda.Stream) -> None:
+        """One step of the reduce of ``G_a`` that runs UNDER the second backward pass (GradCombiner's post-accumulate
+        hooks): every rank calls this once per shard, in the order world-1 .. 0, on a side stream, as soon as the
+        parameters overlapping that shard have their final gradient (or at the latest when the exchange starts). A
+        barrier on the side stream makes sure the shard's range is final on EVERY rank; the shard's owner then launches
+        the first-stage kernel of the tuned three-stage schedule (``x_mode`` 1: ``shard_x`` was reduced even earlier, on
+        the same stream). Uses ``G_a``'s own signal pads, so these barriers cannot collide with the main stream's."""
+        lib = _lib.load()
+        with torch.cuda.stream(stream):
+            self.h_a.barrier(channel=shard, timeout_ms=BARRIER_TIMEOUT_MS)
+            if shard == self.rank:
+                from . import ops
+                self._reduce(lib, ctypes.c_void_p(stream.cuda_stream), self.algo_xpre, 1)
+                ops._count()
+
     def combine(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
-                x_prereduced: bool = False, algo: Optional[str] = None) -> None:
+                x_prereduced: bool = False, algo: Optional[str] = None, reduced: bool = False) -> None:
         """Result lands in every rank's ``g_x``. Stream-ordered; no host synchronisation. With ``x_prereduced`` the
         reduced ``G_x`` shard is already in ``shard_x`` (early reduce-scatter overlapped with the second backward) and
-        only ``G_a`` crosses NVLink in the first kernel. ``algo`` overrides the tuned schedule."""
+        only ``G_a`` crosses NVLink in the first kernel. ``reduced``: the first stage has already run
+        (:meth:`early_reduce_a`, ordered before this call on the current stream): only the scalar barrier and the
+        second stage remain. ``algo`` overrides the tuned schedule."""
         from . import ops
         lib = _lib.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = ctypes.c_void_p
         algo = self._resolve(algo, int(mode), bool(x_prereduced))
         mn, ig = float(max_norm), int(bool(inf_guard))
-        self.h_x.barrier(channel=0)        # every rank's G_x / G_a are complete
+        if not reduced:
+            self.h_x.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)    # every rank's G_x / G_a are complete
         if algo in PIPELINED:
             self._reduce(lib, stream, {"pipe": "p2p", "pipe_nvls": "nvls", "pipe_ce": "ce"}[algo], 2)   # phase 1: G_a, sum a^2
-            self.h_x.barrier(channel=1)    # every rank's sum a^2 is in every slot array
+            self.h_x.barrier(channel=1, timeout_ms=BARRIER_TIMEOUT_MS)    # every rank's sum a^2 is in every slot array
             _lib.check(lib.siss_nvls_xcombine_bcast(P(self.mc_x), self.shard_a.data_ptr(), self.slots1.data_ptr(),
                                                     self.ptrs_s2, self.world, self.rank, self.shard_len, float(value),
                                                     ig, self.ws.data_ptr(), stream), "siss_nvls_xcombine_bcast")
-            self.h_x.barrier(channel=2)    # unclipped combination complete in every G_x; second slot array filled
+            self.h_x.barrier(channel=2, timeout_ms=BARRIER_TIMEOUT_MS)    # unclipped combination complete in every G_x; second slot array filled
             _lib.check(lib.siss_scale_finalize(self.g_x.data_ptr(), self.total, self.slots1.data_ptr(),
                                                self.slots2.data_ptr(), self.world, float(value), mn, ig,
                                                stats.data_ptr(), stream), "siss_scale_finalize")
             ops._count(3)
             return
-        self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
-        self.h_x.barrier(channel=1)        # every rank's scalar slot has been written everywhere
+        if not reduced:
+            self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
+        self.h_x.barrier(channel=1, timeout_ms=BARRIER_TIMEOUT_MS)        # every rank's scalar slot has been written everywhere
         if algo == "ce":
             _lib.check(lib.siss_ce_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
                                                      self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
@@ -239,7 +262,7 @@ class PeerExchange:
                                                       self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
                                                       self.shard_len, int(mode), float(value), mn, ig,
                                                       stats.data_ptr(), stream), "siss_p2p_combine_allgather")
-        self.h_x.barrier(channel=2)        # every rank's shard of the result has landed in every G_x
+        self.h_x.barrier(channel=2, timeout_ms=BARRIER_TIMEOUT_MS)        # every rank's shard of the result has landed in every G_x
         ops._count(2)
 
     # ------------------------------------------------------------------------------------------
