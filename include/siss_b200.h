@@ -355,6 +355,15 @@ int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_p
                           float* shard_x, float* shard_a, double* sums3_local, int x_prereduced,
                           void* workspace, siss_stream_t stream);
 
+/* Region-wise use of the kernels of this section (GradCombiner issues the reduce of each REGION of the flat buffer as
+ * soon as autograd has finalised it, under the second backward pass): call any reduce / gather entry point once per
+ * region with the peer tables pre-offset to the region start and shard_len = the rank's slice of the region — the
+ * kernels address `peer + rank * shard_len + i`, which is then exactly that slice — and the shard pointers offset to the
+ * slice's place. Each such reduce call writes its sums to its own `sums3_local`; siss_publish_sums adds the `regions`
+ * triples in region order and stores the total to doubles [4*rank ..] of every peer's scalar buffer. */
+int siss_publish_sums(const double* region_sums, int regions, double* const* h_peer_scalars, int world, int rank,
+                      siss_stream_t stream);
+
 int siss_p2p_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
                                float* const* h_peers_out, int world, int rank, int64_t shard_len,
                                int mode, float value, float max_norm, int inf_guard, float* stats5,

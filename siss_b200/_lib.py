@@ -57,6 +57,7 @@ SIGNATURES = {
     "siss_batch_stats": (_I, [_P, _P, _P, _P, _L, _L, _P, _P]),
     "siss_p2p_workspace_bytes": (_L, []),
     "siss_p2p_reduce_norm3": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _I, _P, _P]),
+    "siss_publish_sums": (_I, [_P, _I, _P, _I, _I, _P]),
     "siss_p2p_combine_allgather": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _I, _P, _P]),
     "siss_p2p_adamw_allgather": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _I, _P, _P, _D, _D, _D, _D, _D, _L, _P, _P,
                                       _P, _D, _P, _P]),

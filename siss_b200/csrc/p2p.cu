@@ -273,6 +273,20 @@ int siss_p2p_reduce_norm3(const float* const* h_peers_x, const float* const* h_p
     return (int)cudaGetLastError();
 }
 
+// Region-wise exchange (the reduce of each region of the flat buffer is issued as soon as autograd has finalised it):
+// the per-region partial sums of this rank are added in region order and published to slot [rank] of every peer.
+__global__ void publish_sums_kernel(const double* __restrict__ region_sums, int regions, PeerOut pub, int world, int rank) {
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int j = 0; j < regions; ++j) { t0 += region_sums[3 * j]; t1 += region_sums[3 * j + 1]; t2 += region_sums[3 * j + 2]; }
+        for (int r = 0; r < world; ++r) {
+            double* dst = pub.scalars[r] + 4 * rank;
+            dst[0] = t0; dst[1] = t1; dst[2] = t2; dst[3] = 0.0;
+        }
+        __threadfence_system();
+    }
+}
+
 static int launch_combine_allgather(const float* shard_x, const float* shard_a, const double* scalar_slots,
                                     const PeerOut& peers, bool mc, int world, int rank, int64_t shard_len, int mode,
                                     float value, float max_norm, int inf_guard, float* stats5, cudaStream_t st) {
@@ -291,6 +305,19 @@ static int launch_combine_allgather(const float* shard_x, const float* shard_a, 
         default: return SISS_EUNSUPPORTED;
     }
 #undef SISS_CAG
+    return (int)cudaGetLastError();
+}
+
+int siss_publish_sums(const double* region_sums, int regions, double* const* h_peer_scalars, int world, int rank,
+                      siss_stream_t stream) {
+    if (!region_sums || regions < 1 || !h_peer_scalars || world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
+        return SISS_EINVAL;
+    PeerOut pub{};
+    for (int r = 0; r < world; ++r) {
+        if (!h_peer_scalars[r]) return SISS_EINVAL;
+        pub.scalars[r] = h_peer_scalars[r];
+    }
+    publish_sums_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(region_sums, regions, pub, world, rank);
     return (int)cudaGetLastError();
 }
 

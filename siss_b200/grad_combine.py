@@ -71,8 +71,11 @@ class GradCombiner:
             self.offsets.append(off)
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.num_params = sum(p.numel() for p in self.params)
-        quantum = _ALIGN * self.world
-        self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's shard is 16B aligned
+        # Regions: the flat buffers are cut into R equal regions whose G_a reduce is issued as soon as autograd has
+        # finalised them (begin_a); rank r owns slice r of every region. R = 1 switches the overlap off.
+        self._regions_req = max(1, min(64, int(os.environ.get("SISS_OVERLAP_REGIONS", "4")))) if self.world > 1 else 1
+        quantum = _ALIGN * self.world * self._regions_req
+        self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's slice of every region is 16B aligned
         self.peer = None
         self.tuning = {}
         peer_names = ("p2p", "nvls", "ce", "pipe", "pipe_nvls", "pipe_ce")
@@ -138,26 +141,28 @@ class GradCombiner:
         if self.world > 1 and transport == "auto" and self.peer is not None:
             self._autotune()
         # Overlap of the G_a reduce with the second backward pass (peer / multicast / DMA transports): see begin_a().
-        self._early_a = False          # this optimiser step's G_a reduce is being issued shard by shard on the side stream
+        self._early_a = False          # this optimiser step's G_a reduce is being issued region by region on the side stream
         self._armed = False
-        self._overlap = (self.peer is not None and os.environ.get("SISS_NO_OVERLAP") != "1")
-        if self._overlap:
-            S = self.shard_len
-            self._param_shards = [list(range(o // S, min((o + max(p.numel(), 1) - 1) // S, self.world - 1) + 1))
-                                  for o, p in zip(self.offsets, self.params)]
-            self._shard_nparams = [0] * self.world
-            for ks in self._param_shards:
-                for k in ks:
-                    self._shard_nparams[k] += 1
+        self.regions = 1
+        if self.peer is not None and not self._nccl_xpre and self._regions_req > 1 and os.environ.get("SISS_NO_OVERLAP") != "1":
+            self.regions = self._regions_req
+            self.peer.set_regions(self.regions)
+            per = self.total // self.regions
+            self._param_regions = [list(range(o // per, min((o + max(p.numel(), 1) - 1) // per, self.regions - 1) + 1))
+                                   for o, p in zip(self.offsets, self.params)]
+            self._region_nparams = [0] * self.regions
+            for js in self._param_regions:
+                for j in js:
+                    self._region_nparams[j] += 1
             import weakref
             me = weakref.ref(self)                 # the hooks must not keep a discarded combiner (and its buffers) alive
 
-            def _hook(_p, i):
+            def _hook(i):
                 cb = me()
                 if cb is not None:
                     cb._on_grad(i)
             for i, prm in enumerate(self.params):
-                prm.register_post_accumulate_grad_hook(lambda _p, i=i: _hook(_p, i))
+                prm.register_post_accumulate_grad_hook(lambda _p, i=i: _hook(i))
         self._point(self._views_x)   # start out accumulating into G_x (needed by the after_backward_* spelling)
 
     # ------------------------------------------------------------------------------------------
@@ -224,18 +229,27 @@ class GradCombiner:
             ready.record(torch.cuda.current_stream(self.device))      # backward #1 fully enqueued before this point
             with torch.cuda.stream(self._side):
                 self._side.wait_event(ready)
-                dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
+                if self.regions > 1:
+                    # region layout: this rank's slice of every region, back to back (one grouped NCCL launch)
+                    with dist._coalescing_manager(group=self.group, async_ops=False):
+                        for v in self.peer.region_views:
+                            dist.reduce_scatter_tensor(self._shard_x[v["shard_off"]:v["shard_off"] + v["slice_len"]],
+                                                       self.g_x[v["start"]:v["start"] + v["slice_len"] * self.world],
+                                                       op=dist.ReduceOp.SUM, group=self.group)
+                else:
+                    dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
                 self._early_done.record(self._side)
             self._early_x = True
-            if self._overlap and not self._nccl_xpre:
-                # ... and G_a's reduce follows it on the same side stream, shard by shard, UNDER backward #2: a
-                # post-accumulate hook on every parameter counts down the parameters overlapping each rank's shard of the
-                # flat buffer; as soon as shard k (k = world-1 .. 0: autograd finishes the last-registered parameters
-                # first) is final, every rank enqueues a barrier for it and its owner launches the first-stage kernel
-                # (PeerExchange.early_reduce_a). Whatever has not fired by the time the exchange is called (parameters
-                # without a gradient, the first-registered layers) is flushed there, in the same order on every rank.
-                self._pending = list(self._shard_nparams)
-                self._next_shard = self.world - 1
+            if self.regions > 1:
+                # ... and G_a's reduce follows it on the same side stream, region by region, UNDER backward #2: a
+                # post-accumulate hook on every parameter counts down the parameters overlapping each region of the flat
+                # buffer; as soon as region j (j = R-1 .. 0: autograd finishes the last-registered parameters first) is
+                # final, every rank enqueues a barrier for it and reduces its slice of it (PeerExchange.early_reduce_a) —
+                # all ranks at once, so both directions of every link are busy. Whatever has not fired by the time the
+                # exchange is called (parameters without a gradient, the first-registered layers) is flushed there, in
+                # the same order on every rank.
+                self._pending = list(self._region_nparams)
+                self._next_region = self.regions - 1
                 self._armed = True
                 self._early_a = True
 
@@ -289,24 +303,25 @@ class GradCombiner:
         """post-accumulate-grad hook of parameter i (runs on autograd's thread while backward() blocks the caller)."""
         if not self._armed:
             return
-        for k in self._param_shards[i]:
-            self._pending[k] -= 1
+        for j in self._param_regions[i]:
+            self._pending[j] -= 1
         self._issue_ready(torch.cuda.current_stream(self.device))
 
     def _issue_ready(self, producer: torch.cuda.Stream, flush: bool = False) -> None:
-        while self._next_shard >= 0 and (flush or self._pending[self._next_shard] <= 0):
+        while self._next_region >= 0 and (flush or self._pending[self._next_region] <= 0):
             ev = torch.cuda.Event()
-            ev.record(producer)                   # the accumulation that completed this shard is enqueued before this point
+            ev.record(producer)                   # the accumulation that completed this region is enqueued before this point
             self._side.wait_event(ev)
-            self.peer.early_reduce_a(self._next_shard, self._side)
-            self._next_shard -= 1
+            self.peer.early_reduce_a(self._next_region, self._side)
+            self._next_region -= 1
 
     def _finish_early_a(self) -> None:
-        """Called when the exchange starts: flush the shards whose hooks have not fired, then order the caller's stream
-        after the side stream. From here on the first stage of the exchange is done."""
+        """Called when the exchange starts: flush the regions whose hooks have not fired, publish the summed norms, then
+        order the caller's stream after the side stream. From here on the first stage of the exchange is done."""
         cur = torch.cuda.current_stream(self.device)
         self._issue_ready(cur, flush=True)
         self._armed = False
+        self.peer.finish_early_reduce(self._side)
         self._early_done.record(self._side)
         cur.wait_event(self._early_done)
 

@@ -81,6 +81,10 @@ class FusedCombineAdamW:
         self.ema_cfg = None if ema is None else dict(ema)
         # EMAModel.__init__: shadow = clone(params). Sharded: this rank's slice only (gathered on demand).
         self.ema_flat = self.p_shard.clone() if ema is not None else None
+        # The fused two-term step of a combiner that reduces region by region (GradCombiner.regions > 1) keeps this rank's
+        # state in the REGION layout: slice r of every region, back to back, instead of one contiguous range. Decided at
+        # the first step (the single-term path keeps the contiguous layout); the two cannot be mixed in one run.
+        self._region_layout = False
         self.cur_ema_decay = 0.0
         self.d_sched = None
         if device_schedule:
@@ -103,7 +107,13 @@ class FusedCombineAdamW:
     # EMAModel.store / copy_to / restore, used around evaluation (delete_celeb.py:380-382) — not on the hot path
     def ema_copy_to_params(self) -> None:
         self._stored = self.p_flat.clone()
-        if self.sharded:
+        if self.sharded and self._region_layout:
+            import torch.distributed as dist
+            cb = self.combiner
+            for v in cb.peer.region_views:
+                dist.all_gather_into_tensor(self.p_flat[v["start"]:v["start"] + v["slice_len"] * cb.world],
+                                            self.ema_flat[v["shard_off"]:v["shard_off"] + v["slice_len"]], group=cb.group)
+        elif self.sharded:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.p_flat, self.ema_flat, group=self.combiner.group)
         else:
@@ -152,6 +162,13 @@ class FusedCombineAdamW:
                 raise ValueError("give exactly one of scaling_norm= or eta= (or single_term=True)")
             if self.fused_gather and not single_term:
                 # peer-memory transport: two fused kernels — reduce-scatter x2 + K4a | K4b + AdamW/EMA + parameter all-gather
+                if cb.regions > 1 and not self._region_layout:
+                    if self.step_count != 0:
+                        raise RuntimeError("FusedCombineAdamW: single-term and two-term steps cannot be mixed in one run when "
+                                           "the combiner reduces region by region (set SISS_OVERLAP_REGIONS=1)")
+                    if self.ema_flat is not None:
+                        self.ema_flat = cb.peer.shard_slices(self.p_flat)       # shadow = params, in the region layout
+                    self._region_layout = True
                 self.step_count += 1
                 if self.ema_cfg is not None:
                     if self.d_sched is None:
@@ -176,6 +193,9 @@ class FusedCombineAdamW:
                 cb._dirty_x = False
                 cb._point(cb._views_x)
                 return cb.stats
+            if self._region_layout:
+                raise RuntimeError("FusedCombineAdamW: single-term and two-term steps cannot be mixed in one run when the "
+                                   "combiner reduces region by region (set SISS_OVERLAP_REGIONS=1)")
             sums = cb.reduce_to_shards(single_term)
             if single_term:
                 self._launch(sums, SISS_COMBINE_NONE, 0.0, mn, False, two_term=False, shard=True)

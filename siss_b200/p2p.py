@@ -102,6 +102,10 @@ class PeerExchange:
         self.sums_local = torch.zeros(3, dtype=f64, device=device)
         self.ws = torch.zeros(_lib.load().siss_p2p_workspace_bytes(), dtype=torch.uint8, device=device)
         self._staging = None       # DMA landing area of the copy-engine schedules (allocated on first use)
+        self.regions = 1
+        self._whole = self._make_view(0, total)
+        self.region_views = [self._whole]
+        self.region_sums = torch.zeros(3 * 64, dtype=f64, device=device)      # per-region partial sums of this rank
         self.algo = "p2p"          # schedule used when combine() is not told otherwise (see tune())
         self.algo_xpre = "p2p"     # ... when G_x arrives already reduced (three-stage schedules only)
         self.algo3 = "p2p"         # ... best three-stage schedule of the full exchange (EraseDiff cannot be pipelined)
@@ -110,6 +114,35 @@ class PeerExchange:
         dist.barrier(group=self.group)
 
     # ------------------------------------------------------------------------------------------
+    def _make_view(self, start: int, length: int) -> dict:
+        """Pointer tables for the sub-range [start, start + length) of the flat buffers, to be passed to the kernels with
+        shard_len = length / world: they address ``peer + rank * shard_len + i``, i.e. this rank's slice of the range."""
+        arr = ctypes.c_void_p * self.world
+        off = 4 * start
+        v = {"start": start, "slice_len": length // self.world, "shard_off": start // self.world,
+             "ptrs_x": arr(*[int(p) + off for p in self.h_x.buffer_ptrs]),
+             "ptrs_a": arr(*[int(p) + off for p in self.h_a.buffer_ptrs]),
+             "mc_x": self.mc_x + off if self.mc_x else 0, "mc_a": self.mc_a + off if self.mc_a else 0}
+        if getattr(self, "h_p", None) is not None:
+            v["ptrs_p"] = arr(*[int(p) + off for p in self.h_p.buffer_ptrs])
+            v["mc_p"] = self.mc_p + off if self.mc_p else 0
+        return v
+
+    def set_regions(self, regions: int) -> None:
+        """Cut the flat buffers into ``regions`` equal contiguous regions; rank r then owns slice r of EVERY region (its
+        shard buffers hold the slices back to back). Used by GradCombiner to reduce ``G_a`` region by region under the
+        second backward pass, and by the fused ZeRO-1 optimiser step, whose state then lives in this layout."""
+        if regions < 1 or regions > 64 or self.total % (4 * self.world * regions) != 0:
+            raise ValueError("flat buffer length must be a multiple of 4 * world * regions (1 <= regions <= 64)")
+        self.regions = regions
+        per = self.total // regions
+        self.region_views = [self._make_view(j * per, per) for j in range(regions)] if regions > 1 else [self._whole]
+
+    def shard_slices(self, flat: torch.Tensor) -> torch.Tensor:
+        """This rank's shard of a flat buffer in the current layout (region slices back to back) — a copy."""
+        return torch.cat([flat[v["start"] + self.rank * v["slice_len"]: v["start"] + (self.rank + 1) * v["slice_len"]]
+                          for v in self.region_views])
+
     def available(self) -> Sequence[str]:
         return ALGOS if self.has_multicast else tuple(a for a in ALGOS if a not in NEEDS_MULTICAST)
 
@@ -143,28 +176,43 @@ class PeerExchange:
         self.ptrs_p = (ctypes.c_void_p * self.world)(*[int(p) for p in self.h_p.buffer_ptrs])
         assert int(self.ptrs_p[self.rank]) == self.p_flat.data_ptr(), "symmetric-memory pointer table does not match"
         self.mc_p = int(getattr(self.h_p, "multicast_ptr", 0) or 0)
+        self._whole = self._make_view(0, self.total)
+        self.set_regions(self.regions)
         torch.cuda.synchronize(self.g_x.device)
         dist.barrier(group=self.group)
         return self.p_flat
 
     # ------------------------------------------------------------------------------------------
-    def _reduce(self, lib, stream, algo: str, x_mode: int) -> None:
+    def _reduce(self, lib, stream, algo: str, x_mode: int, view: Optional[dict] = None, sums_ptr: Optional[int] = None) -> None:
+        """First stage on the whole buffer (default) or on one region ``view`` (its sums then go to ``sums_ptr``)."""
         P = ctypes.c_void_p
+        v = self._whole if view is None else view
+        sx = P(self.shard_x.data_ptr() + 4 * v["shard_off"])
+        sa = P(self.shard_a.data_ptr() + 4 * v["shard_off"])
+        sums = P(self.sums_local.data_ptr() if sums_ptr is None else sums_ptr)
         if algo == "ce":
-            _lib.check(lib.siss_ce_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
-                                                self.shard_len, self.staging.data_ptr(), self.shard_x.data_ptr(),
-                                                self.shard_a.data_ptr(), self.sums_local.data_ptr(), x_mode, CE_CHUNKS,
+            _lib.check(lib.siss_ce_reduce_norm3(v["ptrs_x"], v["ptrs_a"], self.ptrs_s, self.world, self.rank, v["slice_len"],
+                                                self.staging.data_ptr(), sx, sa, sums, x_mode, CE_CHUNKS,
                                                 self.ws.data_ptr(), stream), "siss_ce_reduce_norm3")
         elif algo == "nvls":
-            _lib.check(lib.siss_nvls_reduce_norm3(P(self.mc_x), P(self.mc_a), self.ptrs_s, self.world, self.rank,
-                                                  self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                                  self.sums_local.data_ptr(), x_mode, self.ws.data_ptr(), stream),
+            _lib.check(lib.siss_nvls_reduce_norm3(P(v["mc_x"]), P(v["mc_a"]), self.ptrs_s, self.world, self.rank,
+                                                  v["slice_len"], sx, sa, sums, x_mode, self.ws.data_ptr(), stream),
                        "siss_nvls_reduce_norm3")
         else:
-            _lib.check(lib.siss_p2p_reduce_norm3(self.ptrs_x, self.ptrs_a, self.ptrs_s, self.world, self.rank,
-                                                 self.shard_len, self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                                 self.sums_local.data_ptr(), x_mode, self.ws.data_ptr(), stream),
+            _lib.check(lib.siss_p2p_reduce_norm3(v["ptrs_x"], v["ptrs_a"], self.ptrs_s, self.world, self.rank,
+                                                 v["slice_len"], sx, sa, sums, x_mode, self.ws.data_ptr(), stream),
                        "siss_p2p_reduce_norm3")
+
+    def _reduce_regions(self, lib, stream, algo: str, x_mode: int) -> None:
+        """First stage region by region (the fused optimiser's layout), then the total of the per-region sums is
+        published to every peer."""
+        for j, v in enumerate(self.region_views):
+            self._reduce(lib, stream, algo, x_mode, view=v, sums_ptr=self.region_sums.data_ptr() + 24 * j)
+        self._publish(lib, stream)
+
+    def _publish(self, lib, stream) -> None:
+        _lib.check(lib.siss_publish_sums(self.region_sums.data_ptr(), self.regions, self.ptrs_s, self.world, self.rank, stream),
+                   "siss_publish_sums")
 
     def adamw_allgather(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
                         exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, ema_shard: Optional[torch.Tensor],
@@ -184,37 +232,50 @@ class PeerExchange:
         # "ce": DMA reduce, then the peer-store kernel for the fused update + parameter all-gather
         if not reduced:
             self.h_x.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)
-            self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
+            if self.regions > 1:
+                self._reduce_regions(lib, stream, algo, 1 if x_prereduced else 0)
+            else:
+                self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
         self.h_x.barrier(channel=1, timeout_ms=BARRIER_TIMEOUT_MS)
-        tail = (int(mode), float(value), float(max_norm), int(bool(inf_guard)),
-                P(exp_avg.data_ptr()), P(exp_avg_sq.data_ptr()), float(lr), float(betas[0]), float(betas[1]), float(eps),
-                float(weight_decay), int(step), P(d_step.data_ptr()), P(0 if d_sched is None else d_sched.data_ptr()),
-                P(0 if ema_shard is None else ema_shard.data_ptr()), float(ema_decay), P(stats.data_ptr()), stream)
-        if algo == "nvls":
-            _lib.check(lib.siss_nvls_adamw_allgather(
-                self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), P(self.mc_p),
-                P(self.p_flat.data_ptr()), self.world, self.rank, self.shard_len, *tail), "siss_nvls_adamw_allgather")
-        else:
-            _lib.check(lib.siss_p2p_adamw_allgather(
-                self.shard_x.data_ptr(), self.shard_a.data_ptr(), self.scalars.data_ptr(), self.ptrs_p, self.world,
-                self.rank, self.shard_len, *tail), "siss_p2p_adamw_allgather")
+        for v in self.region_views:          # one launch per region (one in all when the buffer is not cut)
+            o = 4 * v["shard_off"]
+            tail = (int(mode), float(value), float(max_norm), int(bool(inf_guard)),
+                    P(exp_avg.data_ptr() + o), P(exp_avg_sq.data_ptr() + o), float(lr), float(betas[0]), float(betas[1]),
+                    float(eps), float(weight_decay), int(step), P(d_step.data_ptr()),
+                    P(0 if d_sched is None else d_sched.data_ptr()), P(0 if ema_shard is None else ema_shard.data_ptr() + o),
+                    float(ema_decay), P(stats.data_ptr()), stream)
+            sx, sa = P(self.shard_x.data_ptr() + o), P(self.shard_a.data_ptr() + o)
+            if algo == "nvls":
+                _lib.check(lib.siss_nvls_adamw_allgather(
+                    sx, sa, self.scalars.data_ptr(), P(v["mc_p"]), P(self.p_flat.data_ptr() + 4 * v["start"]), self.world,
+                    self.rank, v["slice_len"], *tail), "siss_nvls_adamw_allgather")
+            else:
+                _lib.check(lib.siss_p2p_adamw_allgather(
+                    sx, sa, self.scalars.data_ptr(), v["ptrs_p"], self.world, self.rank, v["slice_len"], *tail),
+                    "siss_p2p_adamw_allgather")
         self.h_x.barrier(channel=2, timeout_ms=BARRIER_TIMEOUT_MS)        # every rank's parameter shard has landed in every p_flat
-        ops._count(2)
+        ops._count(1 + len(self.region_views))
 
-    def early_reduce_a(self, shard: int, stream: torch.cuda.Stream) -> None:
+    def early_reduce_a(self, region: int, stream: torch.cuda.Stream) -> None:
         """One step of the reduce of ``G_a`` that runs UNDER the second backward pass (GradCombiner's post-accumulate
-        hooks): every rank calls this once per shard, in the order world-1 .. 0, on a side stream, as soon as the
-        parameters overlapping that shard have their final gradient (or at the latest when the exchange starts). A
-        barrier on the side stream makes sure the shard's range is final on EVERY rank; the shard's owner then launches
-        the first-stage kernel of the tuned three-stage schedule (``x_mode`` 1: ``shard_x`` was reduced even earlier, on
-        the same stream). Uses ``G_a``'s own signal pads, so these barriers cannot collide with the main stream's."""
+        hooks): every rank calls this once per region, in the order regions-1 .. 0, on a side stream, as soon as the
+        parameters overlapping that region have their final gradient (or at the latest when the exchange starts). A
+        barrier on the side stream makes sure the region is final on EVERY rank; then every rank reduces its slice of
+        it with the first-stage kernel of the tuned three-stage schedule (``x_mode`` 1: ``shard_x`` was reduced even
+        earlier, on the same stream), all ranks at once — both directions of every link busy. Uses ``G_a``'s own signal
+        pads, so these barriers cannot collide with the main stream's."""
+        from . import ops
         lib = _lib.load()
+        v = self.region_views[region]
         with torch.cuda.stream(stream):
-            self.h_a.barrier(channel=shard, timeout_ms=BARRIER_TIMEOUT_MS)
-            if shard == self.rank:
-                from . import ops
-                self._reduce(lib, ctypes.c_void_p(stream.cuda_stream), self.algo_xpre, 1)
-                ops._count()
+            self.h_a.barrier(channel=region, timeout_ms=BARRIER_TIMEOUT_MS)
+            self._reduce(lib, ctypes.c_void_p(stream.cuda_stream), self.algo_xpre, 1, view=v,
+                         sums_ptr=self.region_sums.data_ptr() + 24 * region)
+        ops._count()
+
+    def finish_early_reduce(self, stream: torch.cuda.Stream) -> None:
+        """After the last region: publish the total of the per-region sums to every peer (side stream)."""
+        self._publish(_lib.load(), ctypes.c_void_p(stream.cuda_stream))
 
     def combine(self, mode: int, value: float, max_norm: float, inf_guard: bool, stats: torch.Tensor,
                 x_prereduced: bool = False, algo: Optional[str] = None, reduced: bool = False) -> None:
@@ -243,27 +304,34 @@ class PeerExchange:
                                                stats.data_ptr(), stream), "siss_scale_finalize")
             ops._count(3)
             return
+        # A G_x shard that was reduced early lives in the region layout (slice r of every region), so whenever it is used
+        # both stages run once per region; otherwise on the whole shard.
+        by_region = self.regions > 1 and (reduced or x_prereduced)
         if not reduced:
-            self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
+            if by_region:
+                self._reduce_regions(lib, stream, algo, 1)
+            else:
+                self._reduce(lib, stream, algo, 1 if x_prereduced else 0)
         self.h_x.barrier(channel=1, timeout_ms=BARRIER_TIMEOUT_MS)        # every rank's scalar slot has been written everywhere
-        if algo == "ce":
-            _lib.check(lib.siss_ce_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                                     self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
-                                                     self.shard_len, CE_CHUNKS, int(mode), float(value), mn, ig,
-                                                     stats.data_ptr(), stream), "siss_ce_combine_allgather")
-            ops._count(CE_CHUNKS - 1)      # one kernel per piece on both sides
-        elif algo == "nvls":
-            _lib.check(lib.siss_nvls_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                                       self.scalars.data_ptr(), P(self.mc_x), self.world, self.rank,
-                                                       self.shard_len, int(mode), float(value), mn, ig,
-                                                       stats.data_ptr(), stream), "siss_nvls_combine_allgather")
-        else:
-            _lib.check(lib.siss_p2p_combine_allgather(self.shard_x.data_ptr(), self.shard_a.data_ptr(),
-                                                      self.scalars.data_ptr(), self.ptrs_x, self.world, self.rank,
-                                                      self.shard_len, int(mode), float(value), mn, ig,
-                                                      stats.data_ptr(), stream), "siss_p2p_combine_allgather")
+        views = self.region_views if by_region else [self._whole]
+        for v in views:
+            o = 4 * v["shard_off"]
+            sx, sa = P(self.shard_x.data_ptr() + o), P(self.shard_a.data_ptr() + o)
+            if algo == "ce":
+                _lib.check(lib.siss_ce_combine_allgather(sx, sa, self.scalars.data_ptr(), v["ptrs_x"], self.world, self.rank,
+                                                         v["slice_len"], CE_CHUNKS, int(mode), float(value), mn, ig,
+                                                         stats.data_ptr(), stream), "siss_ce_combine_allgather")
+                ops._count(CE_CHUNKS - 1)      # one kernel per piece on both sides
+            elif algo == "nvls":
+                _lib.check(lib.siss_nvls_combine_allgather(sx, sa, self.scalars.data_ptr(), P(v["mc_x"]), self.world,
+                                                           self.rank, v["slice_len"], int(mode), float(value), mn, ig,
+                                                           stats.data_ptr(), stream), "siss_nvls_combine_allgather")
+            else:
+                _lib.check(lib.siss_p2p_combine_allgather(sx, sa, self.scalars.data_ptr(), v["ptrs_x"], self.world,
+                                                          self.rank, v["slice_len"], int(mode), float(value), mn, ig,
+                                                          stats.data_ptr(), stream), "siss_p2p_combine_allgather")
         self.h_x.barrier(channel=2, timeout_ms=BARRIER_TIMEOUT_MS)        # every rank's shard of the result has landed in every G_x
-        ops._count(2)
+        ops._count(1 + len(views))
 
     # ------------------------------------------------------------------------------------------
     def tune(self, extra: Optional[Dict[str, Callable[[bool], None]]] = None, iters: int = 7,
