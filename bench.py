@@ -764,7 +764,7 @@ def run_siss(args):
         # collectives, chosen by --transport or (auto) by a start-up measurement on these very buffers
         holder = torch.nn.Parameter(torch.empty(P, device=dev))
         comb = GradCombiner([holder], transport=args.transport)
-        assert comb.total == Ptot
+        Ptot = comb.total                         # padded so that every rank's slice of every region is 16-byte aligned
         transport = comb.transport
         G_x, G_a = comb.g_x, comb.g_a
         G_x.copy_(torch.randn(Ptot, generator=gen, device=dev) * 1e-3)

@@ -97,11 +97,11 @@ def _worker(rank, world, port, q, P):
                     pe = probe.peer
                     pe.g_x.zero_(); pe.g_a.zero_()
                     pe.g_x[:P].copy_(gx); pe.g_a[:P].copy_(ga)
-                    if xpre:    # the rank-ordered reduced shard, as an early reduce-scatter would have left it
-                        pe.shard_x.zero_()
-                        lo, hi = rank * S, min((rank + 1) * S, P)
-                        if hi > lo:
-                            pe.shard_x[:hi - lo].copy_(X[lo:hi])
+                    if xpre:    # the rank-ordered reduced shard, as an early reduce-scatter would have left it: this
+                        Xp = torch.zeros(probe.total, device=dev)       # rank's slice of every region, back to back
+                        Xp[:P].copy_(X)
+                        pe.shard_x.copy_(pe.shard_slices(Xp))
+                        del Xp
                     pe.combine(mode, value, 1.0, False, probe.stats, x_prereduced=xpre, algo=algo)
                     used = pe._resolve(algo, mode, xpre)
                     name = f"{algo}/{case}/{'xpre' if xpre else 'full'}(ran {used})"
