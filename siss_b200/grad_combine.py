@@ -38,7 +38,7 @@ _ALIGN = 4  # parameters start on 16-byte boundaries inside the flat buffers
 
 class GradCombiner:
     def __init__(self, params: Iterable[torch.nn.Parameter], process_group: Optional[dist.ProcessGroup] = None,
-                 distributed: Optional[bool] = None, transport: str = "auto"):
+                 distributed: Optional[bool] = None, transport: str = "auto", overlap_regions: Optional[int] = None):
         """``transport`` selects how the data-parallel exchange is carried when world > 1:
         ``"p2p"`` fused peer-memory kernels over NVLink (csrc/p2p.cu); ``"nvls"`` the same through the NVSwitch's
         in-fabric reduction / replication (multimem, csrc/nvls.cu); ``"ce"`` bytes moved by the copy engines, SMs on
@@ -47,7 +47,13 @@ class GradCombiner:
         ``"nccl"`` torch.distributed collectives around K4a/K4b (one grouped reduce-scatter);
         ``"auto"`` every schedule the node supports AND the NCCL collectives are timed on the real buffers at
         construction (max over ranks, so the choice is collective) and the fastest is kept — separately for the
-        full exchange and for the exchange whose G_x shard was reduced early (siss_b200/p2p.py::PeerExchange.tune)."""
+        full exchange and for the exchange whose G_x shard was reduced early (siss_b200/p2p.py::PeerExchange.tune).
+
+        ``overlap_regions`` (default: ``SISS_OVERLAP_REGIONS`` or 1 = off; peer / multicast / DMA transports): cut the
+        flat buffers into that many regions and issue the reduce of ``G_a`` region by region UNDER the second backward
+        pass, driven by post-accumulate hooks (see :meth:`begin_a`). Opt-in: with the stand-in UNets of this repository
+        it was measured slower than the plain exchange — the kernels it hides are link-bound but still
+        occupy every SM next to the backward pass."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradCombiner needs at least one parameter that requires grad")
@@ -73,7 +79,8 @@ class GradCombiner:
         self.num_params = sum(p.numel() for p in self.params)
         # Regions: the flat buffers are cut into R equal regions whose G_a reduce is issued as soon as autograd has
         # finalised them (begin_a); rank r owns slice r of every region. R = 1 switches the overlap off.
-        self._regions_req = max(1, min(64, int(os.environ.get("SISS_OVERLAP_REGIONS", "4")))) if self.world > 1 else 1
+        req = int(os.environ.get("SISS_OVERLAP_REGIONS", "1")) if overlap_regions is None else int(overlap_regions)
+        self._regions_req = max(1, min(64, req)) if self.world > 1 else 1
         quantum = _ALIGN * self.world * self._regions_req
         self.total = (off + quantum - 1) // quantum * quantum  # padded so every rank's slice of every region is 16B aligned
         self.peer = None

@@ -32,7 +32,7 @@ def _batch(Bg):
             torch.randn(Bg, 1, 16, 16, generator=g), torch.randint(300, 1000, (Bg,), generator=g))
 
 
-def _run_opt(rank, world, Bg, transport="auto", shard=None):
+def _run_opt(rank, world, Bg, transport="auto", shard=None, regions=None):
     """Three optimiser steps with the fused combine+AdamW (+EMA) under data parallel; returns the final parameters
     followed by the EMA shadow parameters. ``shard``: ZeRO-1 optimiser sharding (None = the transport's default)."""
     from siss_b200 import parallel
@@ -43,7 +43,7 @@ def _run_opt(rank, world, Bg, transport="auto", shard=None):
     torch.backends.cudnn.allow_tf32 = False
     dev = torch.device("cuda", rank if world > 1 else 0)
     net = TinyNet().to(dev)
-    comb = GradCombiner(net.parameters(), transport=transport)
+    comb = GradCombiner(net.parameters(), transport=transport, overlap_regions=regions)
     opt = FusedCombineAdamW(comb, lr=3e-3, betas=(0.95, 0.999), weight_decay=1e-2, ema=dict(decay=0.9),
                             shard_optimizer=shard)
     if world > 1:
@@ -72,7 +72,7 @@ def _run_opt(rank, world, Bg, transport="auto", shard=None):
     return torch.cat([final, shadow])
 
 
-def _run(rank, world, Bg, G, transport="auto"):
+def _run(rank, world, Bg, G, transport="auto", regions=None):
     from siss_b200 import parallel
     from siss_b200.grad_combine import GradCombiner
     from siss_b200.scheduler import SissDDPMScheduler
@@ -80,7 +80,7 @@ def _run(rank, world, Bg, G, transport="auto"):
     torch.backends.cudnn.allow_tf32 = False
     dev = torch.device("cuda", rank if world > 1 else 0)
     net = TinyNet().to(dev)
-    comb = GradCombiner(net.parameters(), transport=transport)
+    comb = GradCombiner(net.parameters(), transport=transport, overlap_regions=regions)
     if world > 1 and transport != "auto":
         assert comb.transport == transport
     step = UnlearnStep(net, SissDDPMScheduler(), comb, loss_fn="importance_sampling_with_mixture",
@@ -112,6 +112,11 @@ def _worker(rank, world, port, q):
         out[transport + "/fused_adamw"] = _run_opt(rank, world, 8, transport)
         if transport in ("nccl", "p2p"):
             out[transport + "/fused_adamw_replicated"] = _run_opt(rank, world, 8, transport, shard=False)
+        if transport in ("p2p", "ce") or (transport == "nvls"):
+            # G_a reduced region by region under the second backward pass (post-accumulate hooks), region layout of the
+            # ZeRO-1 state incl. the EMA shadow
+            out[transport + "/regions2"] = _run(rank, world, 8, 2, transport, regions=2)
+            out[transport + "/regions2/fused_adamw"] = _run_opt(rank, world, 8, transport, regions=2)
     if rank == 0:
         q.put(out)
     dist.barrier()

@@ -112,8 +112,12 @@ def _worker(rank, world, port, q, P):
 
         # transports through the public GradCombiner API (NCCL collectives; the auto-tuned choice), incl. the early
         # reduce-scatter of G_x that UnlearnStep issues during the second backward pass
-        for transport in ("nccl", "auto"):
-            comb = GradCombiner([param], transport=transport)
+        for transport in ("nccl", "auto", "auto/regions4"):
+            # "auto/regions4": the G_a reduce issued region by region on the side stream (GradCombiner(overlap_regions=4));
+            # no backward pass runs here, so every region is flushed when the exchange starts — same kernels, same layout
+            comb = GradCombiner([param], transport=transport.split("/")[0], overlap_regions=4 if "/" in transport else None)
+            if "/" in transport and comb.peer is not None and not comb._nccl_xpre:
+                assert comb.regions == 4
             if transport == "auto":
                 report["auto_tuning_ms"] = dict(comb.tuning)
                 report["auto_choice"] = {"full": comb.transport, "nccl_full": comb._nccl_full, "nccl_xpre": comb._nccl_xpre,
