@@ -30,6 +30,21 @@ TWO_TERM = ("importance_sampling_with_mixture", "double_forward_with_neg_del", "
 ONE_TERM = ("naive_del", "simple_neg_del")
 
 
+def _dual_mse(px: torch.Tensor, pa: torch.Tensor, tgt_x: torch.Tensor, tgt_a: torch.Tensor, go_x: float, go_a: float):
+    """``ops.dual_mse_fwd_bwd`` with eager's type promotion: a 16-bit UNet output against an fp32 target is computed in
+    fp32 and the gradients are rounded back to the prediction dtype, as autograd does (rare: accelerate's autocast
+    wrapper returns fp32 predictions); a 16-bit target of another 16-bit kind than the prediction is widened to fp32."""
+    if tgt_x.dtype != tgt_a.dtype:
+        wide = torch.promote_types(tgt_x.dtype, tgt_a.dtype)
+        tgt_x, tgt_a = tgt_x.to(wide), tgt_a.to(wide)
+    if px.dtype != torch.float32 and tgt_x.dtype != px.dtype:
+        if tgt_x.dtype != torch.float32:
+            tgt_x, tgt_a = tgt_x.float(), tgt_a.float()
+        g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(px.float(), pa.float(), tgt_x, tgt_a, go_x, go_a)
+        return g_x.to(px.dtype), g_a.to(pa.dtype), rl_x, rl_a
+    return ops.dual_mse_fwd_bwd(px, pa, tgt_x, tgt_a, go_x, go_a)
+
+
 def upstream_scale(train_batch_size: int, grad_accum_steps: int) -> float:
     """d(total)/d(weighted_loss element) exactly as autograd forms it for
     ``(w.sum() / train_batch_size / G).backward()``: fp32(fp32(1/G) / train_batch_size)."""
@@ -186,8 +201,7 @@ class UnlearnStep:
         pred = self.unet(x_sel, timesteps, **cond, return_dict=False)[0]
         go_x = float(np.float32(self.go) * np.float32(coef))
         p = pred.detach()
-        tgt = noise if noise.dtype == p.dtype or p.dtype == torch.float32 else noise.to(torch.promote_types(noise.dtype, p.dtype))
-        g_x, g_a, rl, _ = ops.dual_mse_fwd_bwd(p, p, tgt, tgt, go_x, self.go)
+        g_x, g_a, rl, _ = _dual_mse(p, p, noise, noise, go_x, self.go)
         m = keep.to(device=p.device, dtype=torch.bool).view(-1, *([1] * (p.dim() - 1)))
         any_keep = m.any()
         zero = torch.zeros((), dtype=g_x.dtype, device=p.device)
@@ -226,14 +240,7 @@ class UnlearnStep:
                 # kernel takes one target dtype, so both go to the WIDER one — never round fp32 noise down to 16 bits
                 wide = torch.promote_types(tgt_x.dtype, tgt_a.dtype)
                 tgt_x, tgt_a = tgt_x.to(wide), tgt_a.to(wide)
-            px, pa = pred_x.detach(), pred_a.detach()
-            if px.dtype != torch.float32 and tgt_x.dtype == torch.float32:
-                # 16-bit UNet output against an fp32 target: eager computes the loss in fp32 and autograd rounds the
-                # gradient back to the prediction dtype — same here (rare: accelerate's autocast returns fp32)
-                g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(px.float(), pa.float(), tgt_x, tgt_a, self.go, self.go)
-                g_x, g_a = g_x.to(px.dtype), g_a.to(pa.dtype)
-            else:
-                g_x, g_a, rl_x, rl_a = ops.dual_mse_fwd_bwd(px, pa, tgt_x, tgt_a, self.go, self.go)
+            g_x, g_a, rl_x, rl_a = _dual_mse(pred_x.detach(), pred_a.detach(), tgt_x, tgt_a, self.go, self.go)
         cb.begin_x()
         torch.autograd.backward(pred_x, g_x)
         cb.begin_a(last_micro_step=last)
@@ -251,8 +258,8 @@ class UnlearnStep:
             alpha = -float(self.superfactor)
         pred = self.unet(xt, timesteps, **cond, return_dict=False)[0]
         # grad = (go * alpha) * 2 (pred - eps): dual kernel with the second term switched off
-        g, _unused, rl, _ = ops.dual_mse_fwd_bwd(pred.detach(), pred.detach(), noise, noise,
-                                                 float(np.float32(self.go) * np.float32(alpha)), 0.0)
+        g, _unused, rl, _ = _dual_mse(pred.detach(), pred.detach(), noise, noise,
+                                      float(np.float32(self.go) * np.float32(alpha)), 0.0)
         self.combiner.begin_x()
         torch.autograd.backward(pred, g)
         out["row_loss_a" if self.loss_fn == "simple_neg_del" else "row_loss_x"] = rl

@@ -182,13 +182,15 @@ def test_k3_large_batch_takes_the_ldg_path_and_matches_eager(cuda_device):
 
 def test_ldg_kernels_pass_the_parity_suite(cuda_device):
     """The plain-LDG variants of the row kernels (scalar path, K3 at large sizes, SISS_NO_TMA=1) are product
-    code too: re-run the kernel parity tests in a subprocess with the TMA pipeline switched off."""
+    code too: re-run the kernel parity tests in a subprocess with the TMA pipeline switched off — and through the
+    ctypes binding (SISS_BINDING=ctypes), so that both bindings see the whole parity suite (this process uses the torch
+    extension)."""
     import os
     import subprocess
     import sys
     from pathlib import Path
     root = Path(__file__).resolve().parent.parent
-    env = dict(os.environ, SISS_NO_TMA="1")
+    env = dict(os.environ, SISS_NO_TMA="1", SISS_BINDING="ctypes")
     cmd = [sys.executable, "-m", "pytest", str(root / "tests" / "test_kernels_gpu.py"), str(root / "tests" / "test_fuzz_gpu.py"),
            str(root / "tests" / "test_rng_gpu.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=str(root))
