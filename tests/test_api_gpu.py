@@ -3,6 +3,7 @@ way the task loops drive it (delete_celeb.py:580-767), compared with the golden 
 CPU oracle's literal restatement of that loop."""
 import copy
 
+import numpy as np
 import pytest
 import torch
 
@@ -548,3 +549,25 @@ def test_device_feeder_counts_the_handed_out_slot_as_occupied(dev):
     (x2,) = feeder.next()
     torch.cuda.synchronize()
     assert float(x1.mean()) == 1.0 and float(x2.mean()) == 2.0
+
+
+@pytest.mark.parametrize("pred_dtype,noise_dtype", [(torch.bfloat16, torch.float32), (torch.float16, torch.bfloat16),
+                                                     (torch.float32, torch.bfloat16)])
+def test_dual_mse_follows_eager_type_promotion(pred_dtype, noise_dtype, dev):
+    """A 16-bit UNet output against an fp32 (or other 16-bit) target: eager computes (pred - target)^2 in the PROMOTED
+    dtype and autograd rounds the gradient back to the prediction dtype (ddpm_deletion_loss.py:62-66). The fast path must
+    never round the target down to the prediction's 16 bits (advisor finding of round 1)."""
+    from siss_b200.step import _dual_mse
+    g = torch.Generator(device=dev).manual_seed(9)
+    shape = (3, 2, 8, 8)
+    px = torch.randn(shape, device=dev, generator=g).to(pred_dtype).requires_grad_(True)
+    pa = torch.randn(shape, device=dev, generator=g).to(pred_dtype).requires_grad_(True)
+    noise = torch.randn(shape, device=dev, generator=g).to(noise_dtype)
+    go = float(np.float32(1.0) / np.float32(3))
+    g_x, g_a, rl_x, rl_a = _dual_mse(px.detach(), pa.detach(), noise, noise, go, go)
+    lx, la = (px - noise) ** 2, (pa - noise) ** 2                   # eager: promoted dtype
+    (lx.sum() / 3).backward()
+    (la.sum() / 3).backward()
+    assert g_x.dtype == pred_dtype and g_a.dtype == pred_dtype
+    assert torch.equal(g_x, px.grad) and torch.equal(g_a, pa.grad)
+    torch.testing.assert_close(rl_x.double(), lx.detach().double().sum(dim=[1, 2, 3]), rtol=1e-5, atol=1e-6)
