@@ -9,13 +9,15 @@ P = 113,673,219 parameters (google/ddpm-celebahq-256). The UNet itself is outsid
 (BASELINE.json north_star) and is replaced by resident tensors (``value``) or a P-parameter stub (``e2e``).
 
 One "step" = one optimiser step's worth of the hot path:
-    K1oK2 siss_add_noise_mixture -> K3 siss_wmse_fwd_bwd -> [N>1: reduce-scatter G_x, G_a]
-    -> K4a siss_norm3 -> [N>1: all-reduce 3 scalars] -> K4b siss_combine -> [N>1: all-gather]
+    K1oK2 siss_add_noise_mixture -> K3 siss_wmse_fwd_bwd -> K4a siss_norm3 -> K4b siss_combine
+    (N>1: K4 runs inside the data-parallel gradient exchange, GradCombiner.exchange — fused peer-memory /
+    NVSwitch-multicast / copy-engine kernels or NCCL collectives, picked by a start-up measurement; `comm` block)
 
-  value  : samples/s, inputs resident in HBM, only the kernels above (+ NCCL collectives when N>1).
-  e2e    : samples/s through the public API (UnlearnStep + GradCombiner, P-parameter stub UNet, real
-           autograd), images copied host->device from pinned memory and the step's statistics copied
-           device->host every step.
+  value  : samples/s, inputs resident in HBM, only the kernels above.
+  e2e    : samples/s through the public API (DeviceFeeder + UnlearnStep + batch_stats + GradCombiner, P-parameter
+           stub UNet, real autograd), images copied host->device from pinned memory and the step's statistics copied
+           device->host every step; with a stage-by-stage breakdown, a device-RNG variant and a CUDA-graph variant.
+  other_configs : BASELINE.json's other configs (tshirt, No-IS, SD): resident step, e2e and CPU baseline.
   --impl reference : the reference's CPU implementation of the same step (oracle port of the
            reference loop, torch CPU, all host threads) — rank 0 only.
 """
@@ -26,7 +28,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -192,8 +193,6 @@ class ClockSampler:
 
     def __init__(self, device_index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thr = None
         try:
             if device_index < 0:
                 raise RuntimeError("clock sampling disabled (SISS_BENCH_NO_NVML=1)")

@@ -18,9 +18,10 @@ folded ``clip_grad_norm_`` in one 12 B/param pass). The scalars stay on the devi
 synchronises the host.
 
 Data parallel (one process per GPU): samples are independent, so the only exchange is the gradient
-sum. With a process group, :meth:`combine` reduce-scatters ``G_x`` and ``G_a`` (NCCL over NVLink),
-runs K4a on the local 1/N shard, all-reduces the three fp64 scalars the scaling and the clip need,
-runs K4b on the shard and all-gathers the result.
+sum. With a process group, :meth:`combine` sums ``G_x`` and ``G_a`` over the ranks into 1/N shards, runs
+K4a on the shard, exchanges the three fp64 scalars the scaling and the clip need, runs K4b on the shard
+and gathers the result — as fused kernels over NVLink peer memory, NVSwitch multicast or the copy
+engines (siss_b200/p2p.py) or as NCCL collectives, whichever a start-up measurement finds fastest.
 """
 from __future__ import annotations
 
