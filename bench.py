@@ -859,6 +859,28 @@ def run_siss(args):
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed_ms = float(el.item())
     value = B * n * args.steps / (elapsed_ms / 1e3)
+    # supplementary (N = 1): the same resident step replayed from ONE CUDA graph — what is left when the four launches'
+    # gaps are gone (`value` itself stays the eager loop, as in round 1 and as at N > 1)
+    graph_replay = None
+    if n == 1:
+        try:
+            from siss_b200.graph import CapturedStep
+            cap = CapturedStep(resident_step, warmup=2)
+            for _ in range(3):
+                cap.replay()
+            torch.cuda.synchronize()
+            gs, ge = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gs.record()
+            for _ in range(args.steps):
+                cap.replay()
+            ge.record()
+            torch.cuda.synchronize()
+            g_ms = gs.elapsed_time(ge) / args.steps
+            graph_replay = {"ms_per_step": g_ms, "value": B / (g_ms * 1e-3), "unit": UNIT,
+                            "note": "SUPPLEMENTARY: resident step captured once (siss_b200.graph.CapturedStep) and replayed"}
+            del cap
+        except Exception as e:  # supplementary: never lose the bench line
+            graph_replay = {"error": repr(e)}
 
     # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md): s_in = bytes of the latent dtype
     s_in = x0.element_size()
@@ -1040,7 +1062,7 @@ def run_siss(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
-            "roofline": roofline, "comm": comm, "exchange_check": exchange_check,
+            "roofline": roofline, "graph_replay": graph_replay, "comm": comm, "exchange_check": exchange_check,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(), "unlearn_steps": unlearn,
             "unlearn_steps_real_unet": ("UNMEASURED: the second half of BASELINE's metric (unlearn steps/s @1/2/4/8 with the "
