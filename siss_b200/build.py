@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--shared",
+    "--threads", "0",          # compile the translation units in parallel (one per core)
 ]
 
 
