@@ -272,14 +272,14 @@ mixture_kernel(const T* __restrict__ src_x,   // !FUSED: noisy keep batch      F
 }
 
 // TMA-pipelined K2 / K1oK2 (vector path): see bulkpipe.cuh.
-template <typename T, bool FUSED_NOISE, bool RNG = false>
+template <typename T, bool FUSED_NOISE, bool RNG = false, int OCC = 3, int STAGES = 6>
 struct MixtureOp {
     static_assert(!RNG || FUSED_NOISE, "in-kernel noise only makes sense fused with add_noise");
     static constexpr int W = VecTraits<T>::N;
     static constexpr int NIN = RNG ? 2 : 3;   // RNG: eps is generated in registers, only x0 and a0 are streamed
     static constexpr int K = 3;
-    static constexpr int kOcc = 3;
-    static constexpr int kStages = 6;   // 6 x 12 KB = 72 KB per CTA, 3 CTAs/SM
+    static constexpr int kOcc = OCC;
+    static constexpr int kStages = STAGES;   // default 6 x 12 KB = 72 KB per CTA, 3 CTAs/SM (SISS_K12_VARIANT: other shapes, A/B)
     __host__ __device__ static constexpr int ub(int) { return 16; }
     struct Params {
         const T* src_x; const T* src_a; const T* x0; const T* a0; const T* noise;
@@ -358,6 +358,30 @@ static int launch_mixture(const void* src_x, const void* src_a, const void* x0, 
         typename Op::Params p{(const T*)src_x, (const T*)src_a, (const T*)x0, (const T*)a0, (const T*)noise, keep, ts, ac,
                               gamma, sigma, T_steps, lam, one_m, (T*)x_mix, dist_x, dist_a, w_x, w_a,
                               rng, d_draw, elem_offset, (T*)noise_out};
+        if constexpr (FUSED && !RNG) {
+            static const int variant = env_int("SISS_K12_VARIANT", 0);    // A/B knob: ring shape
+            if (variant == 1) {   // 2 CTAs/SM x 9 stages
+                using O1 = MixtureOp<T, FUSED, RNG, 2, 9>;
+                typename O1::Params q{p.src_x, p.src_a, p.x0, p.a0, p.noise, p.keep, p.ts, p.ac, p.gamma, p.sigma, p.T_steps,
+                                      p.lam, p.one_m_lam, p.x_mix, p.dist_x, p.dist_a, p.w_x, p.w_a, p.rng, p.d_draw,
+                                      p.elem_offset, p.noise_out};
+                return launch_pipe<O1>(q, ws, B, D, N, st);
+            }
+            if (variant == 2) {   // 3 CTAs/SM x 4 stages
+                using O2 = MixtureOp<T, FUSED, RNG, 3, 4>;
+                typename O2::Params q{p.src_x, p.src_a, p.x0, p.a0, p.noise, p.keep, p.ts, p.ac, p.gamma, p.sigma, p.T_steps,
+                                      p.lam, p.one_m_lam, p.x_mix, p.dist_x, p.dist_a, p.w_x, p.w_a, p.rng, p.d_draw,
+                                      p.elem_offset, p.noise_out};
+                return launch_pipe<O2>(q, ws, B, D, N, st);
+            }
+            if (variant == 3) {   // 1 CTA/SM x 18 stages
+                using O3 = MixtureOp<T, FUSED, RNG, 1, 18>;
+                typename O3::Params q{p.src_x, p.src_a, p.x0, p.a0, p.noise, p.keep, p.ts, p.ac, p.gamma, p.sigma, p.T_steps,
+                                      p.lam, p.one_m_lam, p.x_mix, p.dist_x, p.dist_a, p.w_x, p.w_a, p.rng, p.d_draw,
+                                      p.elem_offset, p.noise_out};
+                return launch_pipe<O3>(q, ws, B, D, N, st);
+            }
+        }
         return launch_pipe<Op>(p, ws, B, D, N, st);
     }
     if (vec) {

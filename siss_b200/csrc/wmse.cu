@@ -493,14 +493,16 @@ __device__ __forceinline__ void store_pred(TP* p, const float (&f)[W]) {
     }
 }
 
-template <typename TP, typename T>
+// OCC / STAGES: CTAs per SM and ring depth (0 = the default below). Other shapes of the same ~200 KB of shared memory
+// per SM were measured in round 2 through SISS_K3_VARIANT (tools/rowkernel_ab.py) — see launch_wmse_fwd_bwd.
+template <typename TP, typename T, int OCC = 2, int STAGES = 0>
 struct WmseFwdBwdOp {
     static constexpr int W = VecTraits<T>::N;
     static constexpr int PB = W * (int)sizeof(TP);   // pred bytes per unit: 16 or 32
     static constexpr int NIN = 4;
     static constexpr int K = 2;
-    static constexpr int kOcc = 2;
-    static constexpr int kStages = (PB == 32) ? 5 : 6;   // 5 x 20 KB or 6 x 16 KB per CTA, 2 CTAs/SM
+    static constexpr int kOcc = OCC;
+    static constexpr int kStages = STAGES ? STAGES : ((PB == 32) ? 5 : 6);   // 5 x 20 KB or 6 x 16 KB per CTA, 2 CTAs/SM
     __host__ __device__ static constexpr int ub(int i) { return i == 0 ? PB : 16; }
     struct Params {
         const TP* pred; const T* x_mix; const T* x0; const T* a0; const int64_t* ts;
@@ -626,6 +628,25 @@ static int launch_wmse_fwd_bwd(const void* pred, const void* x_mix, const void* 
         using Op = WmseFwdBwdOp<TP, T>;
         typename Op::Params p{(const TP*)pred, (const T*)x_mix, (const T*)x0, (const T*)a0, ts, gamma, sigma, T_steps,
                               w_x, w_a, go_x, go_a, (TP*)grad_x, (TP*)grad_a, row_loss_x, row_loss_a};
+        static const int variant = env_int("SISS_K3_VARIANT", 0);     // A/B knob: ring shape
+        if (variant == 1) {   // 3 CTAs/SM x 3 stages
+            using O1 = WmseFwdBwdOp<TP, T, 3, 3>;
+            typename O1::Params q{p.pred, p.x_mix, p.x0, p.a0, p.ts, p.gamma, p.sigma, p.T_steps, p.w_x, p.w_a, p.go_x, p.go_a,
+                                  p.grad_x, p.grad_a, p.row_loss_x, p.row_loss_a};
+            return launch_pipe<O1>(q, ws, B, D, W, st);
+        }
+        if (variant == 2) {   // 1 CTA/SM x 10 stages
+            using O2 = WmseFwdBwdOp<TP, T, 1, 10>;
+            typename O2::Params q{p.pred, p.x_mix, p.x0, p.a0, p.ts, p.gamma, p.sigma, p.T_steps, p.w_x, p.w_a, p.go_x, p.go_a,
+                                  p.grad_x, p.grad_a, p.row_loss_x, p.row_loss_a};
+            return launch_pipe<O2>(q, ws, B, D, W, st);
+        }
+        if (variant == 3) {   // 2 CTAs/SM x 4 stages
+            using O3 = WmseFwdBwdOp<TP, T, 2, 4>;
+            typename O3::Params q{p.pred, p.x_mix, p.x0, p.a0, p.ts, p.gamma, p.sigma, p.T_steps, p.w_x, p.w_a, p.go_x, p.go_a,
+                                  p.grad_x, p.grad_a, p.row_loss_x, p.row_loss_a};
+            return launch_pipe<O3>(q, ws, B, D, W, st);
+        }
         return launch_pipe<Op>(p, ws, B, D, W, st);
     }
     if (k3_vec_ok<TP, T>(pred, x_mix, x0, a0, D, grad_x, grad_a)) {

@@ -28,6 +28,10 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--filler", choices=["write", "read"], default="write",
+                    help="what keeps the stream busy before each bracket: a 1 GB memset (leaves the 126 MB L2 full of DIRTY "
+                         "lines, like K4b's 455 MB of output before K1oK2 in the real step) or a 1 GB read-only reduction "
+                         "(leaves clean lines)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -67,10 +71,14 @@ def main():
     # A filler that keeps the stream busy (~170 us) while the host enqueues the two bracketed launches: a bracket on an
     # IDLE stream would time the host's ctypes call, not the kernel (first version of this tool: 38 / 77 us instead of
     # 29 / 48). It also flushes L2, like the 2.3 GB of K4 traffic between two steps of bench.py.
-    filler = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    filler = torch.zeros(1 << 30, dtype=torch.uint8, device=dev)
+    filler_i32 = filler.view(torch.int32)
     for i in range(args.iters + 5):
         x0, a0, nz, pred = sets[i % nsets]
-        filler.zero_()
+        if args.filler == "write":
+            filler.zero_()
+        else:
+            filler_i32.max()                    # reads 1 GB, writes one scalar: the L2 ends up full of CLEAN lines
         out = bracket("k12", lambda: ops.add_noise_mixture(x0, a0, nz, keep, t, ac, gamma, sigma, 0.5))
         x_mix, _, _, w_x, w_a = out
         bracket("k3", lambda: ops.wmse_fwd_bwd(pred, x_mix, x0, a0, t, gamma, sigma, w_x, w_a, go, go))
@@ -88,7 +96,7 @@ def main():
     except Exception:
         pass
     knobs = {k: v for k, v in os.environ.items() if k.startswith("SISS_")}
-    print(json.dumps({"tag": args.tag, "knobs": knobs, "B": B, "dtype": args.dtype,
+    print(json.dumps({"tag": args.tag, "filler": args.filler, "knobs": knobs, "B": B, "dtype": args.dtype,
                       "k12_us": med["k12"], "k12_frac": bytes12 / med["k12"] / 1e3 / peak,
                       "k3_us": med["k3"], "k3_frac": bytes3 / med["k3"] / 1e3 / peak,
                       "copy12_us": med["copy12"], "copy3_us": med["copy3"]}), flush=True)
