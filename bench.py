@@ -899,6 +899,18 @@ def run_siss(args):
     per_kernel = {k: {"ms": kernel_ms[k], "alg_bytes": alg_bytes[k], "gbs": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9,
                       "frac": alg_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak} for k in kernels
                   if k != "siss_exchange_combine"}
+    # the same kernels under ncu (profiles/ncu_traffic.json, one --set full capture: caches written back and invalidated
+    # before the launch, no event bracket): the in-step brackets of K1oK2 / K3 also carry the write-back of the previous
+    # kernel's dirty L2 lines, the isolated figures do not
+    try:
+        _ncu = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        for k in per_kernel:
+            us = (_ncu.get(k) or {}).get("duration_us_under_ncu")
+            if us and n == 1:
+                per_kernel[k]["ncu_isolated_ms"] = us * 1e-3
+                per_kernel[k]["frac_ncu_isolated"] = alg_bytes[k] / (us * 1e-6) / 1e9 / peak
+    except Exception:
+        pass
     comm = None
     if n > 1:
         # NVLink reference: peer copy 770 GB/s per direction per GPU (B200_PROFILING.md, measured on this pool; 900 nominal)
@@ -989,7 +1001,8 @@ def run_siss(args):
                 "rejected": None if frac_ok else (f"kernel brackets sum to {share:.3f} of the un-instrumented step after "
                                                   f"{bracket_passes} passes: per-kernel timings disturbed, no frac reported"),
                 "empty_event_bracket_us": empty_bracket_us,
-                "bracket_note": ("per-kernel ms are CUDA-event brackets around single launches in a second timed region; an empty "
+                "bracket_note": ("frac_ncu_isolated / ncu_isolated_ms: the committed ncu capture of the same launch (clean caches, no "
+                                 "bracket). per-kernel ms are CUDA-event brackets around single launches in a second timed region; an empty "
                                  "bracket costs empty_event_bracket_us and is NOT subtracted; ncu durations are in profiles/; "
                                  "copy_same_bytes_ms = a plain D2D copy moving the kernel's algorithmic bytes under the same "
                                  "bracket with L2 flushed (the floor at that size), vs_copy_same_bytes = that / kernel ms"),
