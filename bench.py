@@ -902,11 +902,13 @@ def run_siss(args):
     # the same kernels under ncu (profiles/ncu_traffic.json, one --set full capture: caches written back and invalidated
     # before the launch, no event bracket): the in-step brackets of K1oK2 / K3 also carry the write-back of the previous
     # kernel's dirty L2 lines, the isolated figures do not
+    ncu_shape = (n == 1 and B == 64 and args.params == CELEB_PARAMS and args.res == 256 and args.channels == 3
+                 and args.dtype == "bf16")                  # the shape the capture was taken at
     try:
         _ncu = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
         for k in per_kernel:
             us = (_ncu.get(k) or {}).get("duration_us_under_ncu")
-            if us and n == 1:
+            if us and ncu_shape:
                 per_kernel[k]["ncu_isolated_ms"] = us * 1e-3
                 per_kernel[k]["frac_ncu_isolated"] = alg_bytes[k] / (us * 1e-6) / 1e9 / peak
     except Exception:
