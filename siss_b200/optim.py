@@ -10,8 +10,10 @@ Optional, same launch: the EMA shadow update the reference runs after the optimi
 EMA decay read from device memory so schedules survive CUDA-graph replay (``lr_scheduler.step()``, :770).
 
 Parameters are moved into one flat fp32 buffer (``param.data`` become views, exactly like the gradients);
-the module keeps working unchanged. Under data parallel the exchange happens first (NCCL or the fused
-NVLink kernels of ``GradCombiner``), then every rank applies the identical update.
+the module keeps working unchanged. Under data parallel the step is ZeRO-1 by default: the gradients are reduced
+into 1/N shards (NCCL or the fused NVLink kernels of ``GradCombiner``), every rank updates its shard of parameters,
+moments and EMA shadow, and the PARAMETERS are gathered (by the update kernel's own peer / multicast stores when the
+fused transports are in use).
 """
 from __future__ import annotations
 
@@ -45,8 +47,8 @@ class FusedCombineAdamW:
         shadow copy ``ema_flat`` updated inside the optimiser kernel. ``device_schedule``: keep {lr, ema_decay}
         in a device record (``d_sched``) that the kernel reads, refreshed stream-ordered by :meth:`set_schedule`
         — needed when step() is replayed from a CUDA graph with a changing learning rate / EMA warm-up.
-        ``shard_optimizer`` (data parallel; default: on with the NCCL transport, off with the fused peer-memory
-        transport): ZeRO-1 layout — reduce-scatter the gradients, update only this rank's 1/N shard of parameters,
+        ``shard_optimizer`` (data parallel; default: on for every transport; ``False`` = exchange the combined
+        gradient, then every rank applies the identical full update): ZeRO-1 layout — reduce-scatter the gradients, update only this rank's 1/N shard of parameters,
         moments and EMA shadow, all-gather the PARAMETERS. Same bytes on NVLink as all-gathering the combined
         gradient, but the 40 B/param optimiser pass and the optimiser state shrink by N."""
         self.combiner = combiner
