@@ -1009,6 +1009,11 @@ def run_siss(args):
                                  "copy_same_bytes_ms = a plain D2D copy moving the kernel's algorithmic bytes under the same "
                                  "bracket with L2 flushed (the floor at that size), vs_copy_same_bytes = that / kernel ms"),
                 "kernel_share_of_step": share, "host_enqueue_ms_per_step": host_enqueue_ms,
+                # the whole step against the same peak: algorithmic bytes of all its HBM-bound launches / un-instrumented step time
+                "step": ({"alg_bytes": int(sum(alg_bytes[k] for k in hbm_kernels)),
+                          "gbs": sum(alg_bytes[k] for k in hbm_kernels) / (elapsed_ms / args.steps * 1e-3) / 1e9,
+                          "frac": sum(alg_bytes[k] for k in hbm_kernels) / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak}
+                         if n == 1 else None),
                 "l2_note": ("siss_combine re-reads what siss_norm3 just streamed; siss_norm3 leaves the last SISS_L2_KEEP_MB "
                             "(default 80) MB of the buffers in L2 with an evict_last policy and the combine walks in reverse, so "
                             "~6 % of its algorithmic bytes never reach DRAM and frac may exceed 1. `traffic` is an ncu capture, "
