@@ -285,10 +285,15 @@ class ReferenceGradLoop:
 
 
 def combine_flat(g_x: Tensor, g_a: Tensor, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
-                 max_norm: Optional[float] = 1.0, inf_guard: bool = False):
+                 max_norm: Optional[float] = 1.0, inf_guard: bool = False, loss_scale: Optional[float] = None):
     """The sync-step arithmetic of ``ReferenceGradLoop.sync_step`` on ONE flat tensor pair (what the
     combine amounts to when the model has a single parameter tensor). Returns
-    (grad, norm_x, norm_a, scaling_factor, total_norm, clip_coef)."""
+    (grad, norm_x, norm_a, scaling_factor, total_norm, clip_coef).
+
+    ``loss_scale`` restates the ``mixed_precision: fp16`` run (delete_celeb.py:104,237-242; accelerate==0.27.2 and
+    torch's GradScaler, environment.yml:222 — third party, parity unpinned): ``g_x`` / ``g_a`` are gradients of the
+    SCALED loss; the norms, the scaling factor and the combination (:725-750) are taken on them as they are, then
+    ``accelerator.clip_grad_norm_`` first unscales (``GradScaler.unscale_``: grad *= 1/scale) and then clips (:767)."""
     norm_x = torch.sqrt(torch.norm(g_x, p=2) ** 2)
     norm_a = torch.sqrt(torch.norm(g_a, p=2) ** 2)
     if eta is not None:
@@ -301,6 +306,8 @@ def combine_flat(g_x: Tensor, g_a: Tensor, scaling_norm: Optional[float] = None,
     else:
         s = 0
     grad = g_x - s * g_a
+    if loss_scale is not None:
+        grad = grad * (1.0 / float(loss_scale))
     total_norm = torch.norm(grad, p=2)
     clip = torch.ones((), dtype=grad.dtype)
     if max_norm is not None:

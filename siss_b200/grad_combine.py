@@ -281,12 +281,21 @@ class GradCombiner:
     # ------------------------------------------------------------------------------------------
     def combine(self, scaling_norm: Optional[float] = None, eta: Optional[float] = None,
                 max_norm: Optional[float] = 1.0, inf_guard: bool = False, *, mode: Optional[str] = None,
-                value: Optional[float] = None) -> torch.Tensor:
+                value: Optional[float] = None, loss_scale: Optional[float] = None) -> torch.Tensor:
         """Sync-step combine. Exactly one of ``scaling_norm`` (SISS / No-IS, delete_celeb.py:746) or
         ``eta`` (EraseDiff, :741-742) must be given. Leaves the result in ``param.grad`` (views of
         ``G_x``) for ``optimizer.step()`` and returns the device tensor
         ``[norm_loss_x, norm_loss_a, scaling_factor, total_norm, clip_coef]`` (the first three are the
-        reference's wandb scalars, :748). ``G_a`` is cleared for the next accumulation round."""
+        reference's wandb scalars, :748). ``G_a`` is cleared for the next accumulation round.
+
+        ``loss_scale`` (``mixed_precision: fp16`` runs, delete_celeb.py:104: ``scaler.get_scale()``): the buffers hold
+        gradients of the SCALED loss. As in the reference, norms, scaling factor and combination are taken on them as
+        they are (so the three logged scalars are the reference's fp16 values); the clip that
+        ``accelerator.clip_grad_norm_`` applies AFTER unscaling is applied here to the scaled gradient with the
+        threshold ``max_norm * loss_scale``, and the result is left SCALED in ``param.grad`` — the GradScaler's own
+        ``unscale_`` inside ``optimizer.step()`` (which also does the inf check / step skip) finishes the job. Do not
+        call ``accelerator.clip_grad_norm_`` as well. ``total_norm`` is reported unscaled. Costs nothing: same two
+        kernels, different threshold."""
         if mode is not None:                  # combine(mode="scaling_norm" | "erasediff", value=...) spelling
             if mode not in ("scaling_norm", "erasediff") or value is None or scaling_norm is not None or eta is not None:
                 raise ValueError('mode must be "scaling_norm" or "erasediff", with value= and without scaling_norm= / eta=')
@@ -296,16 +305,29 @@ class GradCombiner:
         mode = SISS_COMBINE_SCALING_NORM if eta is None else SISS_COMBINE_ERASEDIFF
         value = float(scaling_norm if eta is None else eta)
         mn = 0.0 if max_norm is None else float(max_norm)
+        scale = self._check_loss_scale(loss_scale)
+        mn *= scale
         if self.world == 1:
             self._norm3(self.g_x, self.g_a, out=self.sums3)
             self._combine(self.g_x, self.g_a, self.sums3, mode, value, mn, inf_guard, out=self.g_x, stats=self.stats)
         else:
             self.exchange(mode, value, mn, inf_guard)
+        if scale != 1.0:
+            self.stats[3:4].mul_(1.0 / scale)       # total norm of the UNSCALED gradient, what clip_grad_norm_ returns
         self.g_a.zero_()
         self._dirty_x = True
         self._early_x = False
         self._point(self._views_x)
         return self.stats
+
+    @staticmethod
+    def _check_loss_scale(loss_scale: Optional[float]) -> float:
+        if loss_scale is None:
+            return 1.0
+        scale = float(loss_scale)
+        if not (scale > 0.0 and scale != float("inf")):
+            raise ValueError(f"loss_scale must be a positive finite number, got {loss_scale!r}")
+        return scale
 
     def _on_grad(self, i: int) -> None:
         """post-accumulate-grad hook of parameter i (runs on autograd's thread while backward() blocks the caller)."""
@@ -388,20 +410,25 @@ class GradCombiner:
         self._early_x = False
         return self.sums3
 
-    def clip_only(self, max_norm: float = 1.0) -> torch.Tensor:
+    def clip_only(self, max_norm: float = 1.0, loss_scale: Optional[float] = None) -> torch.Tensor:
         """Single-term methods (naive_del / simple_neg_del: ``loss is not None``, delete_celeb.py:682-684):
-        gradients are in ``G_x``; only the data-parallel sum and ``clip_grad_norm_`` apply."""
+        gradients are in ``G_x``; only the data-parallel sum and ``clip_grad_norm_`` apply. ``loss_scale``: as in
+        :meth:`combine` (threshold ``max_norm * loss_scale``, result left scaled for the GradScaler)."""
+        scale = self._check_loss_scale(loss_scale)
+        mn = float(max_norm) * scale
         if self.world == 1:
             self._norm3(self.g_x, self.g_x, out=self.sums3)
-            self._combine(self.g_x, self.g_x, self.sums3, SISS_COMBINE_NONE, 0.0, float(max_norm), False,
+            self._combine(self.g_x, self.g_x, self.sums3, SISS_COMBINE_NONE, 0.0, mn, False,
                           out=self.g_x, stats=self.stats)
         else:
             dist.reduce_scatter_tensor(self._shard_x, self.g_x, op=dist.ReduceOp.SUM, group=self.group)
             self._norm3(self._shard_x, self._shard_x, out=self.sums3)
             dist.all_reduce(self.sums3, op=dist.ReduceOp.SUM, group=self.group)
-            self._combine(self._shard_x, self._shard_x, self.sums3, SISS_COMBINE_NONE, 0.0, float(max_norm),
+            self._combine(self._shard_x, self._shard_x, self.sums3, SISS_COMBINE_NONE, 0.0, mn,
                           False, out=self._shard_x, stats=self.stats)
             dist.all_gather_into_tensor(self.g_x, self._shard_x, group=self.group)
+        if scale != 1.0:
+            self.stats[3:4].mul_(1.0 / scale)
         self._dirty_x = True
         self._point(self._views_x)
         return self.stats

@@ -571,3 +571,43 @@ def test_dual_mse_follows_eager_type_promotion(pred_dtype, noise_dtype, dev):
     assert g_x.dtype == pred_dtype and g_a.dtype == pred_dtype
     assert torch.equal(g_x, px.grad) and torch.equal(g_a, pa.grad)
     torch.testing.assert_close(rl_x.double(), lx.detach().double().sum(dim=[1, 2, 3]), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kw", [dict(scaling_norm=5.0), dict(eta=5.0)])
+def test_grad_combiner_under_a_grad_scaler(kw, dev):
+    """mixed_precision: fp16 (delete_celeb.py:104): a real torch GradScaler around the drop-in loop —
+    scaler.scale(loss).backward() twice, combine(loss_scale=scaler.get_scale()), scaler.step(optimizer) — against the oracle's
+    restatement of the reference's fp16 sequence (norms / factor on scaled gradients, unscale, clip) + a hand-written SGD
+    step. The combined gradient is left scaled; the GradScaler's own unscale inside step() finishes the job."""
+    from helpers import GoldenStepNet
+    from siss_b200.grad_combine import GradCombiner
+    torch.backends.cudnn.allow_tf32 = False
+    B, S, lr = 4, 2.0 ** 12, 0.25
+    net = GoldenStepNet().to(dev)
+    ref = copy.deepcopy(net)
+    torch.manual_seed(21)
+    x = torch.randn(B, 1, 8, 8, device=dev)
+    t = torch.randint(0, 1000, (B,), device=dev)
+    e_x, e_a = torch.randn_like(x) * 20, torch.randn_like(x) * 20       # large targets: the clip is active
+    # reference side: flat gradients of the scaled losses, then the oracle's fp16 sequence
+    flats = []
+    for tgt in (e_x, e_a):
+        loss = ((ref(x, t)[0] - tgt) ** 2).sum() / B
+        gs = torch.autograd.grad(loss * S, list(ref.parameters()))
+        flats.append(torch.cat([g.reshape(-1) for g in gs]).cpu())
+    exp, nx, na, sf, tn, clip = O.combine_flat(flats[0], flats[1], max_norm=1.0, loss_scale=S, **kw)
+    assert float(clip) < 1.0 and float(sf) != 0.0
+    # product side
+    scaler = torch.amp.GradScaler("cuda", init_scale=S)
+    opt = torch.optim.SGD(net.parameters(), lr=lr)
+    comb = GradCombiner(net.parameters())
+    pred = net(x, t)[0]
+    comb.begin_x(); scaler.scale(((pred - e_x) ** 2).sum() / B).backward(retain_graph=True)
+    comb.begin_a(); scaler.scale(((pred - e_a) ** 2).sum() / B).backward()
+    stats = comb.combine(max_norm=1.0, loss_scale=scaler.get_scale(), **kw).clone()
+    before = [p.detach().clone() for p in net.parameters()]
+    scaler.step(opt); scaler.update()
+    assert scaler.get_scale() == S                                        # no inf found, step not skipped
+    got = torch.cat([((b - p.detach()) / lr).reshape(-1) for b, p in zip(before, net.parameters())]).cpu()
+    torch.testing.assert_close(got, exp, rtol=2e-4, atol=2e-6)
+    torch.testing.assert_close(stats.cpu(), torch.stack([nx, na, sf.float(), tn, clip.float()]), rtol=2e-4, atol=1e-7)

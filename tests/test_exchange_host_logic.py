@@ -81,3 +81,52 @@ def test_both_bench_arms_print_one_config():
     w = bench.celeb_workload(args)
     assert w["B"] == 64 and w["chw"] == (3, 256, 256) and w["dt"] == torch.bfloat16
     assert bench.TSHIRT["B"] == 32 and bench.SD["cond"] == (77, 768)
+
+
+# ---- mixed_precision: fp16 (GradScaler) -------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(scaling_norm=5.0), dict(scaling_norm=500.0), dict(eta=0.05)])
+def test_oracle_fp16_sequence_is_the_unscaled_run_with_scaling_norm_divided_by_the_scale(kw):
+    """What the reference does under a GradScaler (oracle.combine_flat(loss_scale=), delete_celeb.py:725-767): norms and
+    scaling factor are taken on SCALED gradients, so for a power-of-two scale S the result is, bit for bit, the unscaled
+    run with scaling_norm / S (EraseDiff's factor is scale-invariant) — the scale dependence INTEGRATION.md §2 describes."""
+    import torch
+    from oracle import siss_oracle as O
+    torch.manual_seed(11)
+    gx, ga = torch.randn(4096) * 3e-2, torch.randn(4096) * 1e-2 + 0.1 * torch.randn(4096) * 3e-2
+    S = 1024.0
+    got = O.combine_flat(gx * S, ga * S, max_norm=1.0, loss_scale=S, **kw)
+    kw_ref = dict(scaling_norm=kw["scaling_norm"] / S) if "scaling_norm" in kw else kw
+    exp = O.combine_flat(gx, ga, max_norm=1.0, **kw_ref)
+    assert torch.equal(got[0], exp[0])
+    assert float(got[4]) == float(exp[4]) and float(got[5]) == float(exp[5])          # total norm, clip coefficient
+    assert float(got[1]) == float(exp[1]) * S and float(got[2]) == float(exp[2]) * S  # the logged norms are the scaled ones
+
+
+@pytest.mark.parametrize("kw,mode,val", [(dict(scaling_norm=5.0), 0, 5.0), (dict(eta=0.05), 1, 0.05)])
+def test_grad_combiner_loss_scale_on_cpu_stand_ins(kw, mode, val):
+    """GradCombiner.combine(loss_scale=S) (host logic; K4a / K4b replaced by the CPU stand-ins): the result, unscaled as the
+    GradScaler does inside optimizer.step(), is the oracle's fp16 sequence; total_norm is reported unscaled; clip_only too."""
+    import torch
+    from oracle import siss_oracle as O
+    from siss_b200.grad_combine import GradCombiner
+    torch.manual_seed(5)
+    prm = torch.nn.Parameter(torch.zeros(3000))
+    comb = GradCombiner([prm], distributed=False)
+    comb._norm3, comb._combine = O.norm3_cpu, O.combine_from_sums_cpu
+    gx, ga = torch.randn(3000) * 4e-2, torch.randn(3000) * 1e-2
+    S = 4096.0
+    comb.g_x[:3000].copy_(gx * S); comb.g_a[:3000].copy_(ga * S)
+    stats = comb.combine(max_norm=1.0, loss_scale=S, **kw).clone()
+    exp, nx, na, s, tn, clip = O.combine_flat(gx * S, ga * S, max_norm=1.0, loss_scale=S, **kw)
+    torch.testing.assert_close(prm.grad * (1.0 / S), exp, rtol=3e-5, atol=1e-9)
+    torch.testing.assert_close(stats, torch.stack([nx, na, s.float(), tn, clip.float()]), rtol=3e-5, atol=1e-7)
+    assert float(stats[4]) < 1.0, "the case must exercise the clip"
+    # single-term
+    comb.begin_x()
+    comb.g_x[:3000].copy_(gx * S)
+    stats = comb.clip_only(1.0, loss_scale=S).clone()
+    tn = torch.norm(gx)
+    torch.testing.assert_close(prm.grad * (1.0 / S), gx * torch.clamp(1.0 / (tn + 1e-6), max=1.0), rtol=3e-5, atol=1e-9)
+    torch.testing.assert_close(stats[3], tn, rtol=3e-5, atol=0)
+    with pytest.raises(ValueError):
+        comb.combine(scaling_norm=5.0, loss_scale=0.0)
