@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--no-real-unet", action="store_true", help="skip the steps/s block around the real UNet architecture")
     ap.add_argument("--no-copy-floor", action="store_true", help="skip the same-bytes D2D copy floor (keeps ncu launch lists clean)")
     ap.add_argument("--cpu-steps", type=int, default=16)
     ap.add_argument("--transport", choices=["auto", "p2p", "nvls", "ce", "pipe", "pipe_nvls", "pipe_ce", "nccl"], default="auto",
@@ -125,10 +126,13 @@ class StandInUNet(torch.nn.Module):
         return (y.float() + self.bank.sum() * 1e-6,)     # fp32 output, as accelerate's autocast wrapper returns
 
 
-def unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist):
-    """Supplementary: full unlearning optimiser steps (forward + two backward passes through a stand-in UNet,
-    SISS loss kernels, gradient exchange, fused combine + AdamW) through the public API, per-GPU batch 16,
-    data resident. Returns steps/s (max over ranks timing)."""
+def unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist, real_arch=False):
+    """Supplementary: full unlearning optimiser steps (forward + two backward passes through a UNet, SISS loss kernels,
+    gradient exchange, fused combine + AdamW) through the public API, per-GPU batch 16, data resident. Returns steps/s
+    (max over ranks timing). ``real_arch``: the UNet is tools/unet2d.py::celebahq256 — a plain-PyTorch restatement of
+    diffusers' UNet2DModel at the google/ddpm-celebahq-256 configuration (exactly 113 673 219 parameters, 497 GFLOP per
+    sample forward at 256x256), random init, bf16 autocast, NCHW as the reference runs it; otherwise the light conv
+    stand-in carrying P parameters."""
     from siss_b200.grad_combine import GradCombiner
     from siss_b200.optim import FusedCombineAdamW
     from siss_b200.step import UnlearnStep
@@ -136,7 +140,14 @@ def unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist):
     shape = (Bs, args.channels, args.res, args.res)
     dt = torch_dtype(args.dtype)
     torch.manual_seed(1234)                                   # identical initial weights on every rank
-    unet = StandInUNet(args.params, ch=args.channels).to(dev)
+    if real_arch:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import unet2d
+        unet = unet2d.celebahq256().to(dev)
+        assert sum(p.numel() for p in unet.parameters()) == CELEB_PARAMS
+        fwd_flops = unet2d.forward_flops(unet, args.res, args.channels)
+    else:
+        unet = StandInUNet(args.params, ch=args.channels).to(dev)
     comb = GradCombiner(unet.parameters(), transport=args.transport)
     opt = FusedCombineAdamW(comb, lr=5e-6, betas=(0.95, 0.999), eps=1e-8, weight_decay=1e-6)   # delete_celeb.yaml:127-134
     step = UnlearnStep(unet, sched, comb, loss_fn="importance_sampling_with_mixture", train_batch_size=Bs * n, lambd=0.5,
@@ -153,10 +164,10 @@ def unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist):
         step._micro = 0
         opt.step(scaling_norm=500.0, max_norm=1.0)
 
-    for _ in range(3):
+    for _ in range(2 if real_arch else 3):
         one()
     barrier()
-    K = 10
+    K = 5 if real_arch else 10
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s_ev.record()
     for _ in range(K):
@@ -172,6 +183,38 @@ def unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist):
            "note": ("SUPPLEMENTARY: full optimiser step through the public API (UnlearnStep + GradCombiner + "
                     "FusedCombineAdamW) with a stand-in conv UNet (diffusers is not installed) carrying "
                     f"P={args.params} parameters; not comparable with the real UNet's absolute steps/s")}
+    if real_arch:
+        # where the step goes: one instrumented pass (events at UnlearnStep's stage marks + around the optimiser step)
+        marks = []
+
+        def hook(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+        step.stage_hook = hook
+        hook("start")
+        nz = torch.randn(shape, dtype=dt, device=dev)
+        ts = torch.randint(999, 1000, (Bs,), device=dev).long()
+        hook("torch_rng")
+        step.micro_step(x0, a0, nz, ts, keep_mask=keep)
+        step._micro = 0
+        opt.step(scaling_norm=500.0, max_norm=1.0)
+        hook("exchange_combine_adamw")
+        torch.cuda.synchronize()
+        step.stage_hook = None
+        stages = {name: a.elapsed_time(b) for (_, a), (name, b) in zip(marks[:-1], marks[1:])}
+        ours = stages.get("k1k2", 0.0) + stages.get("k3", 0.0) + stages.get("exchange_combine_adamw", 0.0)
+        step_flops = 5.0 * fwd_flops * Bs                     # forward + two backward passes (2x forward each)
+        res.update({
+            "unet": "tools/unet2d.py::celebahq256 (UNet2DModel architecture of google/ddpm-celebahq-256, 113 673 219 parameters, "
+                    "random init, bf16 autocast, NCHW)",
+            "unet_forward_gflop_per_sample": fwd_flops / 1e9,
+            "unet_tflops_achieved": step_flops / (ms * 1e-3) / 1e12,
+            "stages_ms": stages, "path_share_of_step": ours / max(sum(stages.values()), 1e-9),
+            "note": ("full optimiser step through the public API (UnlearnStep + GradCombiner + FusedCombineAdamW) around a "
+                     "plain-PyTorch restatement of the checkpoint's UNet2DModel architecture (diffusers itself is not installed; "
+                     "eager cuDNN / SDPA kernels, not ours): forward + two backward passes, K1oK2, K3, exchange, K4 + AdamW; "
+                     "path_share_of_step = (k1k2 + k3 + exchange_combine_adamw) / step from one instrumented pass")})
     del unet, comb, opt, step
     torch.cuda.empty_cache()
     return res
@@ -1046,6 +1089,17 @@ def run_siss(args):
             unlearn = unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist)
         except Exception as e:  # supplementary: never break the bench line
             unlearn = {"error": repr(e)}
+    # ... and the same step around the checkpoint's real UNet architecture (the second half of BASELINE's metric). Every
+    # rank must take the same branch (collectives inside), so the condition depends on the arguments only.
+    unlearn_real = None
+    if (not args.no_extra_configs and not args.no_real_unet and args.params == CELEB_PARAMS and args.res == 256
+            and args.channels == 3):
+        try:
+            torch.cuda.empty_cache()
+            unlearn_real = unlearn_steps_with_standin(args, dev, n, rank, sched, barrier, dist, real_arch=True)
+        except Exception as e:
+            unlearn_real = {"error": repr(e)}
+            torch.cuda.empty_cache()
     others = None
     eager_ref = None
     if rank == 0 and n == 1 and not args.no_extra_configs:
@@ -1085,10 +1139,11 @@ def run_siss(args):
             "roofline": roofline, "graph_replay": graph_replay, "comm": comm, "exchange_check": exchange_check,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(), "unlearn_steps": unlearn,
-            "unlearn_steps_real_unet": ("UNMEASURED: the second half of BASELINE's metric (unlearn steps/s @1/2/4/8 with the "
-                                        "diffusers UNet2DModel / SD UNet) cannot be measured in this image — diffusers is not "
-                                        "installed and there is no network; `unlearn_steps` uses a stand-in conv UNet with the "
-                                        "real parameter count and ~100x fewer FLOPs"),
+            # the second half of BASELINE's metric. diffusers is not installed (no network), so the UNet is a plain-PyTorch
+            # restatement of the checkpoint's architecture (tools/unet2d.py: same blocks, same 113 673 219 parameters, random
+            # init); the SD UNet (860 M, cross-attention) is not restated: UNMEASURED
+            "unlearn_steps_real_unet": unlearn_real if unlearn_real is not None else
+            "UNMEASURED in this run (--no-real-unet / --no-extra-configs / non-celeb shape)",
             "other_configs": others,
             "eager_gpu_reference": eager_ref,
         }
